@@ -1,0 +1,132 @@
+// b200/carray.cuh -- the objects user code strings see inside ElementwiseKernel /
+// ReductionKernel bodies: `raw` arrays (CArray) and the loop indexer (`_ind`).
+// Source-compatible with the names and methods documented for the reference's
+// kernels (cupy/_core/include/cupy/carray.cuh:228-458 CArray, :518-620 CIndexer)
+// -- size(), shape(), strides(), operator[] by linear index or by index array --
+// but written from scratch on top of the launcher's RawView descriptor.
+#pragma once
+#include "base.cuh"
+
+namespace b200 {
+
+struct RawView {
+    char*   data;
+    int64_t size;
+    int32_t ndim;
+    int32_t pad_;
+    int64_t shape[kMaxNdim];
+    int64_t strides[kMaxNdim];   // bytes
+};
+
+}  // namespace b200
+
+// The template signature mirrors the reference so user preambles that spell the
+// type out (rare) still compile; c_contiguous / use_32bit are hints only.
+template <typename T, int _ndim, bool _c_contiguous = false, bool _use_32bit = false>
+class CArray {
+public:
+    static const int ndim = _ndim;
+    typedef ptrdiff_t index_t;
+
+private:
+    T* data_;
+    ptrdiff_t size_;
+    ptrdiff_t shape_[_ndim > 0 ? _ndim : 1];
+    ptrdiff_t strides_[_ndim > 0 ? _ndim : 1];
+
+public:
+    __device__ explicit CArray(const b200::RawView& v)
+        : data_(reinterpret_cast<T*>(v.data)), size_(v.size) {
+#pragma unroll
+        for (int d = 0; d < _ndim; ++d) {
+            shape_[d] = v.shape[d];
+            strides_[d] = v.strides[d];
+        }
+    }
+    __device__ ptrdiff_t size() const { return size_; }
+    __device__ const ptrdiff_t* shape() const { return shape_; }
+    __device__ const ptrdiff_t* strides() const { return strides_; }
+    __device__ T* data() const { return data_; }
+
+    template <typename Int>
+    __device__ T& operator[](const Int (&idx)[_ndim > 0 ? _ndim : 1]) {
+        return const_cast<T&>(const_cast<const CArray&>(*this)[idx]);
+    }
+    template <typename Int>
+    __device__ const T& operator[](const Int (&idx)[_ndim > 0 ? _ndim : 1]) const {
+        const char* p = reinterpret_cast<const char*>(data_);
+#pragma unroll
+        for (int d = 0; d < _ndim; ++d) p += ptrdiff_t(idx[d]) * strides_[d];
+        return *reinterpret_cast<const T*>(p);
+    }
+    __device__ T& operator[](const ptrdiff_t* idx) {
+        return const_cast<T&>(const_cast<const CArray&>(*this)[idx]);
+    }
+    __device__ const T& operator[](const ptrdiff_t* idx) const {
+        const char* p = reinterpret_cast<const char*>(data_);
+#pragma unroll
+        for (int d = 0; d < _ndim; ++d) p += idx[d] * strides_[d];
+        return *reinterpret_cast<const T*>(p);
+    }
+    // linear C-order index
+    __device__ T& operator[](ptrdiff_t i) {
+        return const_cast<T&>(const_cast<const CArray&>(*this)[i]);
+    }
+    __device__ const T& operator[](ptrdiff_t i) const {
+        if (_c_contiguous) return data_[i];
+        const char* p = reinterpret_cast<const char*>(data_);
+#pragma unroll
+        for (int d = _ndim - 1; d > 0; --d) {
+            const ptrdiff_t q = i / shape_[d];
+            p += (i - q * shape_[d]) * strides_[d];
+            i = q;
+        }
+        if (_ndim > 0) p += i * strides_[0];
+        return *reinterpret_cast<const T*>(p);
+    }
+};
+
+template <int _ndim, bool _use_32bit = false>
+class CIndexer {
+public:
+    static const int ndim = _ndim;
+
+private:
+    ptrdiff_t size_;
+    ptrdiff_t shape_[_ndim > 0 ? _ndim : 1];
+    ptrdiff_t index_[_ndim > 0 ? _ndim : 1];
+
+public:
+    __device__ CIndexer(ptrdiff_t size, const int64_t* shape) : size_(size) {
+#pragma unroll
+        for (int d = 0; d < _ndim; ++d) {
+            shape_[d] = shape[d];
+            index_[d] = 0;
+        }
+    }
+    __device__ ptrdiff_t size() const { return size_; }
+    __device__ const ptrdiff_t* shape() const { return shape_; }
+    __device__ const ptrdiff_t* get() const { return index_; }
+    __device__ void set(ptrdiff_t i) {
+#pragma unroll
+        for (int d = _ndim - 1; d > 0; --d) {
+            const ptrdiff_t q = i / shape_[d];
+            index_[d] = i - q * shape_[d];
+            i = q;
+        }
+        if (_ndim > 0) index_[0] = i;
+    }
+};
+
+// Size-only stand-in for `_in_ind` / `_out_ind` inside reduction bodies
+// (user expressions only ever call .size() on them).
+struct CSizeIndexer {
+    ptrdiff_t size_;
+    __device__ ptrdiff_t size() const { return size_; }
+};
+
+#ifndef CUPY_FOR
+#define CUPY_FOR(i, n)                                                        \
+    for (ptrdiff_t i = static_cast<ptrdiff_t>(blockIdx.x) * blockDim.x + threadIdx.x; \
+         i < (n); i += static_cast<ptrdiff_t>(blockDim.x) * gridDim.x)
+#endif

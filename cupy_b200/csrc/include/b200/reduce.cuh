@@ -1,0 +1,286 @@
+// b200/reduce.cuh -- the reduction skeleton: single-pass full, row (segmented)
+// and column kernels over a small functor interface.  The same kernels are
+// instantiated (a) by nvcc for the built-in sum/prod/min/max/arg*/mean/var
+// functors of reduce_ops.cuh and (b) by NVRTC for functors generated from
+// ReductionKernel / create_reduction_func code strings.
+//
+// Functor interface (`Op`):
+//     typedef ... in_t;      element type in memory
+//     typedef ... acc_t;     the reference's `_type_reduce`
+//     typedef ... out_t;     element type of the result in memory
+//     typedef ... index_t;   type of the reduce-axis index `_J` (int or long long)
+//     typedef ... ctx_t;     per-step context shared by the lanes of a thread
+//     acc_t identity() const;
+//     ctx_t step(int count) const;              // count = elements each lane state holds after this step
+//     void  accumulate(acc_t&, const ctx_t&, const in_t&, index_t j) const;   // fold ONE element (j increases per state)
+//     acc_t single(const in_t&, index_t j) const;                             // acc_t of one element (tails)
+//     acc_t combine(const acc_t& a, const acc_t& b) const;                    // a precedes b in index order
+//     out_t post(const acc_t&, long long n_reduce) const;
+//
+// Replaces: the shared-memory tree of cupy/_core/_reduction.pyx:59-112, the CUB
+// block-reduce template of cupy/_core/_cub_reduction.pyx:67-215 (two-pass for
+// full reductions) and the CUB device calls of cupy/cuda/cupy_cub.cu:749-1148.
+#pragma once
+#include "base.cuh"
+
+namespace b200 {
+
+template <class T>
+B200_DEVICE T load_volatile(const T* p) {
+    constexpr int words = sizeof(T) / 4;
+    static_assert(sizeof(T) % 4 == 0, "accumulators are shuffled/copied in 32-bit words");
+    union U { T t; uint32_t w[words]; B200_DEVICE U() {} };
+    U u;
+    const volatile uint32_t* s = reinterpret_cast<const volatile uint32_t*>(p);
+#pragma unroll
+    for (int i = 0; i < words; ++i) u.w[i] = s[i];
+    return u.t;
+}
+
+// Sub-warp combine over GROUP consecutive lanes; result valid in the group's lane 0.
+template <int GROUP, class Op, class T>
+B200_DEVICE T group_combine(const Op& op, T v) {
+#pragma unroll
+    for (int d = GROUP / 2; d > 0; d >>= 1) {
+        T o = shfl_down_any(v, d);
+        v = op.combine(v, o);
+    }
+    return v;
+}
+
+// Merge a thread's lane states in a fixed order.
+template <class Op, int U, int V>
+B200_DEVICE typename Op::acc_t merge_lanes(const Op& op, typename Op::acc_t (&acc)[U][V]) {
+    typename Op::acc_t r = acc[0][0];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            if (u | k) r = op.combine(r, acc[u][k]);
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// FULL: x[n] -> y[0].  Persistent grid; each block folds its tiles into
+// U*V lane states per thread, combines through shuffles + shared memory,
+// publishes one partial, and the LAST block to arrive (atomic ticket) folds the
+// partials in a fixed order -- one launch, one read of x, deterministic result.
+// workspace: gridDim.x partials + a zeroed uint32 ticket (left zeroed).
+// ---------------------------------------------------------------------------
+template <class Op, int VEC, int UNROLL, int THREADS>
+__device__ __forceinline__ void reduce_full_body(
+        const Op& op, const typename Op::in_t* __restrict__ x, typename Op::out_t* __restrict__ y,
+        int64_t n, typename Op::acc_t* partials, uint32_t* ticket) {
+    typedef typename Op::acc_t acc_t;
+    typedef typename Op::index_t index_t;
+    constexpr int64_t kTile = int64_t(THREADS) * VEC * UNROLL;
+    __shared__ acc_t smem[THREADS / 32];
+    __shared__ bool is_last;
+
+    acc_t acc[UNROLL][VEC];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[u][k] = op.identity();
+
+    int count = 0;
+    for (int64_t base = int64_t(blockIdx.x) * kTile; base < n; base += int64_t(gridDim.x) * kTile) {
+        if (base + kTile <= n) {
+            Pack<typename Op::in_t, VEC> v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+                load_pack(v[u], x + base + (int64_t(u) * THREADS + threadIdx.x) * VEC);
+            const typename Op::ctx_t ctx = op.step(++count);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    op.accumulate(acc[u][k], ctx, v[u][k],
+                                  static_cast<index_t>(base + (int64_t(u) * THREADS + threadIdx.x) * VEC + k));
+        } else {
+            for (int64_t i = base + threadIdx.x; i < n; i += THREADS)
+                acc[0][0] = op.combine(acc[0][0], op.single(x[i], static_cast<index_t>(i)));
+        }
+    }
+    acc_t r = merge_lanes<Op, UNROLL, VEC>(op, acc);
+    r = block_combine(op, r, smem);
+
+    if (gridDim.x == 1) {
+        if (threadIdx.x == 0) y[0] = op.post(r, n);
+        return;
+    }
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = r;
+        __threadfence();
+        const uint32_t t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    r = op.identity();
+    for (int i = threadIdx.x; i < int(gridDim.x); i += THREADS)
+        r = op.combine(r, load_volatile(partials + i));
+    r = block_combine(op, r, smem);
+    if (threadIdx.x == 0) {
+        y[0] = op.post(r, n);
+        *ticket = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// ROWS: x[rows][n] (n contiguous) -> y[rows].  GROUP threads cooperate on a row:
+// GROUP == THREADS (a block per row) for long rows, 32 / 8 / 1 for short ones so
+// that small segments still fill the machine.  Grid-stride over rows.
+// Host guarantees for VEC > 1: n % VEC == 0 and 16-byte style alignment of x.
+// ---------------------------------------------------------------------------
+template <class Op, int VEC, int UNROLL, int THREADS, int GROUP>
+__device__ __forceinline__ void reduce_rows_body(
+        const Op& op, const typename Op::in_t* __restrict__ x, typename Op::out_t* __restrict__ y,
+        int64_t rows, int64_t n) {
+    typedef typename Op::acc_t acc_t;
+    typedef typename Op::index_t index_t;
+    constexpr int kRowsPerBlock = THREADS / GROUP;
+    constexpr int64_t kTile = int64_t(GROUP) * VEC * UNROLL;
+    __shared__ acc_t smem[THREADS / 32];
+    const int g = threadIdx.x % GROUP;       // lane within the row group
+    const int gi = threadIdx.x / GROUP;      // which row of the block
+
+    for (int64_t row0 = int64_t(blockIdx.x) * kRowsPerBlock; row0 < rows;
+         row0 += int64_t(gridDim.x) * kRowsPerBlock) {
+        const int64_t row = row0 + gi;
+        const bool live = row < rows;
+        const typename Op::in_t* __restrict__ xr = x + (live ? row : 0) * n;
+        acc_t acc[UNROLL][VEC];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[u][k] = op.identity();
+        if (live) {
+            int count = 0;
+            int64_t base = 0;
+            for (; base + kTile <= n; base += kTile) {
+                Pack<typename Op::in_t, VEC> v[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) load_pack(v[u], xr + base + (int64_t(u) * GROUP + g) * VEC);
+                const typename Op::ctx_t ctx = op.step(++count);
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k)
+                        op.accumulate(acc[u][k], ctx, v[u][k],
+                                      static_cast<index_t>(base + (int64_t(u) * GROUP + g) * VEC + k));
+            }
+            for (int64_t i = base + g; i < n; i += GROUP)
+                acc[0][0] = op.combine(acc[0][0], op.single(xr[i], static_cast<index_t>(i)));
+        }
+        acc_t r = merge_lanes<Op, UNROLL, VEC>(op, acc);
+        if (GROUP == THREADS) {
+            r = block_combine(op, r, smem);
+            if (threadIdx.x == 0) y[row] = op.post(r, n);
+        } else {
+            if (GROUP > 1) r = group_combine<(GROUP > 32 ? 32 : GROUP)>(op, r);
+            if (g == 0 && live) y[row] = op.post(r, n);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// COLS: x[batch][n][cols] (cols contiguous) -> y[batch][cols]: the reduced axis
+// is the STRIDED one.  Block = 8 warps; a warp reads 32*VEC consecutive columns
+// of one row per instruction (full 128-byte lines) and walks down the rows with
+// RU independent loads in flight; the 8 warps' states meet in shared memory.
+// gridDim = (column tiles, row splits, batch).  With more than one row split the
+// split partials go to the workspace and the last block of the column tile
+// (atomic ticket) folds them in row order.
+// workspace: batch*nsplit*cols partials, then batch*gridDim.x zeroed tickets.
+// ---------------------------------------------------------------------------
+template <class Op, int VEC, int RU>
+__device__ __forceinline__ void reduce_cols_body(
+        const Op& op, const typename Op::in_t* __restrict__ x, typename Op::out_t* __restrict__ y,
+        int64_t n, int64_t cols, typename Op::acc_t* partials, uint32_t* tickets) {
+    typedef typename Op::acc_t acc_t;
+    typedef typename Op::index_t index_t;
+    constexpr int kWarps = 8;
+    constexpr int kTileCols = 32 * VEC;
+    __shared__ acc_t smem[kWarps][kTileCols];
+    __shared__ bool is_last;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b = blockIdx.z;
+    const int nsplit = gridDim.y, split = blockIdx.y;
+    const int64_t c0 = (int64_t(blockIdx.x) * 32 + lane) * VEC;
+    const bool col_ok = c0 < cols;     // VEC > 1 => cols % VEC == 0 => whole pack in range
+    const int64_t rows_per_split = (n + nsplit - 1) / nsplit;
+    const int64_t r_begin = int64_t(split) * rows_per_split;
+    const int64_t r_end = (r_begin + rows_per_split < n) ? r_begin + rows_per_split : n;
+    const typename Op::in_t* __restrict__ xb = x + b * n * cols + c0;
+
+    acc_t acc[RU][VEC];
+#pragma unroll
+    for (int u = 0; u < RU; ++u)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[u][k] = op.identity();
+
+    if (col_ok) {
+        int count = 0;
+        int64_t r = r_begin + warp;
+        for (; r + int64_t(RU - 1) * kWarps < r_end; r += int64_t(RU) * kWarps) {
+            Pack<typename Op::in_t, VEC> v[RU];
+#pragma unroll
+            for (int u = 0; u < RU; ++u) load_pack(v[u], xb + (r + int64_t(u) * kWarps) * cols);
+            const typename Op::ctx_t ctx = op.step(++count);
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    op.accumulate(acc[u][k], ctx, v[u][k], static_cast<index_t>(r + int64_t(u) * kWarps));
+        }
+        for (; r < r_end; r += kWarps) {
+            Pack<typename Op::in_t, VEC> v;
+            load_pack(v, xb + r * cols);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                acc[0][k] = op.combine(acc[0][k], op.single(v[k], static_cast<index_t>(r)));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        acc_t a = acc[0][k];
+#pragma unroll
+        for (int u = 1; u < RU; ++u) a = op.combine(a, acc[u][k]);
+        smem[warp][lane * VEC + k] = a;
+    }
+    __syncthreads();
+
+    const int64_t tile_c0 = int64_t(blockIdx.x) * kTileCols;
+    for (int t = threadIdx.x; t < kTileCols; t += blockDim.x) {
+        if (tile_c0 + t >= cols) continue;
+        acc_t a = smem[0][t];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) a = op.combine(a, smem[w][t]);
+        if (nsplit == 1) y[b * cols + tile_c0 + t] = op.post(a, n);
+        else partials[(b * nsplit + split) * cols + tile_c0 + t] = a;
+    }
+    if (nsplit == 1) return;
+
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t t = atomicAdd(&tickets[b * gridDim.x + blockIdx.x], 1u);
+        is_last = (t == uint32_t(nsplit) - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int t = threadIdx.x; t < kTileCols; t += blockDim.x) {
+        if (tile_c0 + t >= cols) continue;
+        acc_t a = load_volatile(partials + (b * nsplit) * cols + tile_c0 + t);
+        for (int s = 1; s < nsplit; ++s)
+            a = op.combine(a, load_volatile(partials + (b * nsplit + s) * cols + tile_c0 + t));
+        y[b * cols + tile_c0 + t] = op.post(a, n);
+    }
+    if (threadIdx.x == 0) tickets[b * gridDim.x + blockIdx.x] = 0u;
+}
+
+}  // namespace b200

@@ -1,0 +1,271 @@
+// reduce_impl.cuh -- prebuilt reductions (sum/prod/min/max/argmin/argmax/mean/var) on
+// the skeleton of b200/reduce.cuh, their launch geometry and dtype dispatch.
+//
+// Entry points replace cupy/cuda/cupy_cub.cu:1083-1159 (cub_device_reduce,
+// cub_device_segmented_reduce + workspace queries) and the generic launch of
+// cupy/_core/_reduction.pyx:239-253, 481-508; op / dtype codes are the
+// reference's (cupy_cub.h:4-11, type_dispatcher.cuh:15-28).
+#include <algorithm>
+
+#pragma once
+#include "common.h"
+#include "include/b200/reduce.cuh"
+#include "include/b200/reduce_ops.cuh"
+
+namespace b200 {
+
+constexpr int kRedThreads = 256;
+// Workspace header: atomic tickets of the single-pass combines.  Zero when the
+// workspace is first handed in; every kernel leaves it zeroed.
+constexpr size_t kTicketBytes = 16384;
+
+template <class Op, int VEC, int UNROLL>
+__global__ void __launch_bounds__(kRedThreads) reduce_full_kernel(
+        Op op, const typename Op::in_t* x, typename Op::out_t* y, int64_t n,
+        typename Op::acc_t* partials, uint32_t* ticket) {
+    reduce_full_body<Op, VEC, UNROLL, kRedThreads>(op, x, y, n, partials, ticket);
+}
+
+template <class Op, int VEC, int UNROLL, int GROUP>
+__global__ void __launch_bounds__(kRedThreads) reduce_rows_kernel(
+        Op op, const typename Op::in_t* x, typename Op::out_t* y, int64_t rows, int64_t n) {
+    reduce_rows_body<Op, VEC, UNROLL, kRedThreads, GROUP>(op, x, y, rows, n);
+}
+
+template <class Op, int VEC, int RU>
+__global__ void __launch_bounds__(kRedThreads) reduce_cols_kernel(
+        Op op, const typename Op::in_t* x, typename Op::out_t* y, int64_t n, int64_t cols,
+        typename Op::acc_t* partials, uint32_t* tickets) {
+    reduce_cols_body<Op, VEC, RU>(op, x, y, n, cols, partials, tickets);
+}
+
+// ---- geometry ---------------------------------------------------------------
+struct Geometry {
+    int vec;                 // chosen vector width
+    unsigned gx, gy, gz;
+    int group;               // ROWS
+    size_t partial_count;    // accumulators in the workspace
+    size_t ticket_count;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <int FULLVEC>
+static int pick_vec(const void* x, int64_t inner, int itemsize) {
+    int vec = FULLVEC;
+    for (; vec > 1; vec >>= 1)
+        if (reinterpret_cast<uintptr_t>(x) % (uintptr_t(vec) * itemsize) == 0 && inner % vec == 0) break;
+    return vec;
+}
+
+static int full_grid(int64_t n, int vec, int unroll, int sm) {
+    const int64_t tile = int64_t(kRedThreads) * vec * unroll;
+    const int64_t tiles = (n + tile - 1) / tile;
+    return int(std::max<int64_t>(1, std::min<int64_t>(tiles, int64_t(sm) * 8)));
+}
+
+static int rows_group(int64_t n, int vec) {
+    if (n >= 2048) return kRedThreads;
+    if (n >= int64_t(32) * vec) return 32;
+    if (n >= int64_t(8) * vec) return 8;
+    return 1;
+}
+
+static void cols_geometry(int64_t batch, int64_t n, int64_t cols, int vec, int sm, Geometry* g) {
+    const int64_t tiles = (cols + 32 * vec - 1) / (32 * vec);
+    // enough blocks for ~8 per SM, at least 64 rows per split
+    int64_t want = (int64_t(sm) * 8 + tiles * batch - 1) / (tiles * batch);
+    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>(want, n / 64));
+    nsplit = std::min<int64_t>(nsplit, 65535);
+    g->gx = unsigned(tiles);
+    g->gy = unsigned(nsplit);
+    g->gz = unsigned(batch);
+    g->partial_count = nsplit > 1 ? size_t(batch) * nsplit * cols : 0;
+    g->ticket_count = nsplit > 1 ? size_t(batch) * tiles : 0;
+}
+
+// ---- typed launch -------------------------------------------------------------
+template <class Op, int FULLVEC>
+static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, void* yv,
+                     void* ws, size_t ws_bytes, cudaStream_t stream, bool query, size_t* need) {
+    typedef typename Op::in_t in_t;
+    typedef typename Op::out_t out_t;
+    typedef typename Op::acc_t acc_t;
+    DeviceInfo di = {148, 10, 0, 0};
+    if (!query) {
+        int st = device_info(&di);
+        if (st) return st;
+    }
+    const in_t* x = static_cast<const in_t*>(xv);
+    out_t* y = static_cast<out_t*>(yv);
+    constexpr int U = FULLVEC >= 8 ? 2 : 4;    // lane states per thread = U * VEC <= 16
+    // COLS keeps 8 warps x 32*VEC accumulators in shared memory: cap it at 32 KiB
+    constexpr int CV = (8 * 32 * FULLVEC * int(sizeof(acc_t)) > 32768) ? FULLVEC / 2 : FULLVEC;
+    constexpr int CU = CV >= 8 ? 2 : 4;
+
+    if (d->layout == B200_RED_FULL) {
+        // workspace = [tickets: kTicketBytes][partials]; sized for the widest grid
+        const size_t partial_bytes = size_t(di.sm_count) * 8 * sizeof(acc_t);
+        if (query) { *need = kTicketBytes + align_up(size_t(296) * 8 * sizeof(acc_t), 16); return 0; }
+        const int vec = pick_vec<FULLVEC>(x, d->n_reduce, sizeof(in_t));
+        const int grid = full_grid(d->n_reduce, vec, U, di.sm_count);
+        if (grid > 1 && ws_bytes < kTicketBytes + partial_bytes)
+            return fail(B200_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, kTicketBytes + partial_bytes);
+        uint32_t* ticket = static_cast<uint32_t*>(ws);
+        acc_t* partials = reinterpret_cast<acc_t*>(static_cast<char*>(ws) + kTicketBytes);
+        if (vec == FULLVEC)
+            reduce_full_kernel<Op, FULLVEC, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket);
+        else
+            reduce_full_kernel<Op, 1, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket);
+    } else if constexpr (Op::kWideIndex) {
+        // (value, 64-bit index) pairs are only built for FULL; the host routes
+        // rows/cols with >= 2^31 reduced elements elsewhere
+        return fail(B200_E_UNSUPPORTED, "reduced extent >= 2^31 is only prebuilt for the FULL layout");
+    } else if (d->layout == B200_RED_ROWS) {
+        if (query) { *need = 0; return 0; }
+        const int vec = pick_vec<FULLVEC>(x, d->n_reduce, sizeof(in_t));
+        const int v = (vec == FULLVEC) ? FULLVEC : 1;
+        const int group = rows_group(d->n_reduce, v);
+        const int64_t rows_per_block = kRedThreads / group;
+        const int64_t blocks = (d->n_out + rows_per_block - 1) / rows_per_block;
+        const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>(blocks, int64_t(di.sm_count) * 64)));
+#define B200_ROWS(V, G) reduce_rows_kernel<Op, V, U, G><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_out, d->n_reduce)
+        if (v == FULLVEC) {
+            if (group == kRedThreads) B200_ROWS(FULLVEC, kRedThreads);
+            else if (group == 32) B200_ROWS(FULLVEC, 32);
+            else if (group == 8) B200_ROWS(FULLVEC, 8);
+            else B200_ROWS(FULLVEC, 1);
+        } else {
+            if (group == kRedThreads) B200_ROWS(1, kRedThreads);
+            else if (group == 32) B200_ROWS(1, 32);
+            else if (group == 8) B200_ROWS(1, 8);
+            else B200_ROWS(1, 1);
+        }
+#undef B200_ROWS
+    } else if (d->layout == B200_RED_COLS) {
+        Geometry g = {};
+        if (query) {
+            // worst case over vector widths (tickets live in the fixed header)
+            cols_geometry(d->batch, d->n_reduce, d->n_out, 1, 296, &g);
+            Geometry g2 = {};
+            cols_geometry(d->batch, d->n_reduce, d->n_out, CV, 296, &g2);
+            const size_t pc = std::max(g.partial_count, g2.partial_count);
+            *need = pc ? kTicketBytes + align_up(pc * sizeof(acc_t), 16) : 0;
+            return 0;
+        }
+        int vec = pick_vec<CV>(x, d->n_out, sizeof(in_t));
+        if (vec != CV) vec = 1;
+        cols_geometry(d->batch, d->n_reduce, d->n_out, vec, di.sm_count, &g);
+        if (g.ticket_count * sizeof(uint32_t) > kTicketBytes) {   // cannot happen: splits only when tiles*batch < 8*SMs
+            g.gy = 1; g.partial_count = 0; g.ticket_count = 0;
+        }
+        const size_t pbytes = g.partial_count * sizeof(acc_t);
+        if (g.partial_count && ws_bytes < kTicketBytes + pbytes)
+            return fail(B200_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, kTicketBytes + pbytes);
+        uint32_t* tickets = static_cast<uint32_t*>(ws);
+        acc_t* partials = reinterpret_cast<acc_t*>(static_cast<char*>(ws) + kTicketBytes);
+        const dim3 grid(g.gx, g.gy, g.gz);
+        if (vec == CV)
+            reduce_cols_kernel<Op, CV, CU><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, d->n_out, partials, tickets);
+        else
+            reduce_cols_kernel<Op, 1, 4><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, d->n_out, partials, tickets);
+    } else {
+        return fail(B200_E_INVALID, "bad reduction layout %d", d->layout);
+    }
+    B200_CUDA_TRY(cudaPeekAtLastError());
+    return 0;
+}
+
+// ---- dtype dispatch -----------------------------------------------------------
+// accumulator / result rules: cupy/_core/_routines_math.pyx:762-807 (sum, prod),
+// cupy/_core/_routines_statistics.pyx:128-146 (mean), :556-600 (var)
+template <class T> struct sum_acc { typedef T type; };
+template <> struct sum_acc<bool> { typedef long long type; };
+template <> struct sum_acc<int8_t> { typedef long long type; };
+template <> struct sum_acc<int16_t> { typedef long long type; };
+template <> struct sum_acc<int32_t> { typedef long long type; };
+template <> struct sum_acc<uint8_t> { typedef unsigned long long type; };
+template <> struct sum_acc<uint16_t> { typedef unsigned long long type; };
+template <> struct sum_acc<uint32_t> { typedef unsigned long long type; };
+template <> struct sum_acc<float16> { typedef float type; };
+
+template <class T> struct sum_out { typedef typename sum_acc<T>::type type; };
+template <> struct sum_out<float16> { typedef float16 type; };
+
+template <class T> struct mom_float { typedef double type; };   // ints: float64
+template <> struct mom_float<float> { typedef float type; };
+template <> struct mom_float<float16> { typedef float type; };
+template <class T> struct mom_out { typedef double type; };
+template <> struct mom_out<float> { typedef float type; };
+template <> struct mom_out<float16> { typedef float16 type; };
+
+template <class T> struct out_id;
+template <> struct out_id<long long> { static constexpr int v = B200_TYPE_INT64; };
+template <> struct out_id<unsigned long long> { static constexpr int v = B200_TYPE_UINT64; };
+template <> struct out_id<float16> { static constexpr int v = B200_TYPE_FLOAT16; };
+template <> struct out_id<float> { static constexpr int v = B200_TYPE_FLOAT32; };
+template <> struct out_id<double> { static constexpr int v = B200_TYPE_FLOAT64; };
+template <> struct out_id<int32_t> { static constexpr int v = B200_TYPE_INT32; };
+template <> struct out_id<int8_t> { static constexpr int v = B200_TYPE_INT8; };
+template <> struct out_id<uint8_t> { static constexpr int v = B200_TYPE_UINT8; };
+template <> struct out_id<int16_t> { static constexpr int v = B200_TYPE_INT16; };
+template <> struct out_id<uint16_t> { static constexpr int v = B200_TYPE_UINT16; };
+template <> struct out_id<uint32_t> { static constexpr int v = B200_TYPE_UINT32; };
+template <> struct out_id<bool> { static constexpr int v = B200_TYPE_BOOL; };
+
+#define B200_REQUIRE_OUT(T)                                                                         \
+    if (d->out_dtype != out_id<T>::v)                                                               \
+        return fail(B200_E_UNSUPPORTED, "op %d in dtype %d: prebuilt result dtype is %d, asked %d", \
+                    d->op, d->in_dtype, out_id<T>::v, d->out_dtype)
+
+template <class T>
+static int run_for_type(const b200_reduce_desc_t* d, const void* x, void* y, void* ws, size_t wsb,
+                        cudaStream_t s, bool query, size_t* need) {
+    constexpr int FV = (16 / int(sizeof(T))) > 8 ? 8 : (16 / int(sizeof(T)));
+    // index type of arg-reductions: 32 bit whenever the reduced extent allows
+    const bool j32 = d->n_reduce < (int64_t(1) << 31);
+    switch (d->op) {
+        case B200_OP_SUM: {
+            typedef typename sum_acc<T>::type A; typedef typename sum_out<T>::type O;
+            B200_REQUIRE_OUT(O);
+            return run_typed<SumOp<T, A, O>, FV>(SumOp<T, A, O>(), d, x, y, ws, wsb, s, query, need);
+        }
+        case B200_OP_PROD: {
+            typedef typename sum_acc<T>::type A; typedef typename sum_out<T>::type O;
+            B200_REQUIRE_OUT(O);
+            return run_typed<ProdOp<T, A, O>, FV>(ProdOp<T, A, O>(), d, x, y, ws, wsb, s, query, need);
+        }
+        case B200_OP_MIN:
+            B200_REQUIRE_OUT(T);
+            if (j32) return run_typed<ExtremumOp<T, T, int, false, false>, FV>(ExtremumOp<T, T, int, false, false>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<ExtremumOp<T, T, long long, false, false>, FV>(ExtremumOp<T, T, long long, false, false>(), d, x, y, ws, wsb, s, query, need);
+        case B200_OP_MAX:
+            B200_REQUIRE_OUT(T);
+            if (j32) return run_typed<ExtremumOp<T, T, int, true, false>, FV>(ExtremumOp<T, T, int, true, false>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<ExtremumOp<T, T, long long, true, false>, FV>(ExtremumOp<T, T, long long, true, false>(), d, x, y, ws, wsb, s, query, need);
+        case B200_OP_ARGMIN:
+            B200_REQUIRE_OUT(long long);
+            if (j32) return run_typed<ExtremumOp<T, long long, int, false, true>, FV>(ExtremumOp<T, long long, int, false, true>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<ExtremumOp<T, long long, long long, false, true>, FV>(ExtremumOp<T, long long, long long, false, true>(), d, x, y, ws, wsb, s, query, need);
+        case B200_OP_ARGMAX:
+            B200_REQUIRE_OUT(long long);
+            if (j32) return run_typed<ExtremumOp<T, long long, int, true, true>, FV>(ExtremumOp<T, long long, int, true, true>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<ExtremumOp<T, long long, long long, true, true>, FV>(ExtremumOp<T, long long, long long, true, true>(), d, x, y, ws, wsb, s, query, need);
+        case B200_OP_MEAN: {
+            typedef typename mom_float<T>::type F; typedef typename mom_out<T>::type O;
+            B200_REQUIRE_OUT(O);
+            return run_typed<MeanOp<T, F, O>, FV>(MeanOp<T, F, O>(), d, x, y, ws, wsb, s, query, need);
+        }
+        case B200_OP_VAR: {
+            typedef typename mom_float<T>::type F; typedef typename mom_out<T>::type O;
+            B200_REQUIRE_OUT(O);
+            MomentsOp<T, F, O, true> op;
+            op.ddof = F(d->param);
+            return run_typed<MomentsOp<T, F, O, true>, FV>(op, d, x, y, ws, wsb, s, query, need);
+        }
+        default:
+            return fail(B200_E_INVALID, "op code %d is not a reduction", d->op);
+    }
+}
+
+}  // namespace b200
