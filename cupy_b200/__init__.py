@@ -1,0 +1,28 @@
+"""cupy_b200 -- a B200-native (sm_100a) implementation of CuPy's data-parallel
+engine: ufunc / ElementwiseKernel launcher, ReductionKernel / axis reductions and
+the cumsum scan, behind CuPy's own Python surface.  See DESIGN.md.
+
+Importing this package loads libcupy_b200.so and fails loudly if it is missing:
+there is no CPU or NumPy fallback.
+"""
+from cupy_b200 import _lib  # noqa: F401  (loads the C-ABI library; ImportError if absent)
+from cupy_b200._lib import B200Error, CompileException  # noqa: F401
+from cupy_b200._core._ndarray import (  # noqa: F401
+    ndarray, AxisError, empty, empty_like, zeros, zeros_like, ones, ones_like, full, arange,
+    asarray, array, asnumpy, from_torch, from_cuda_array_interface, empty_pinned)
+from cupy_b200._core._kernel import (  # noqa: F401
+    ElementwiseKernel, ufunc, create_ufunc, elementwise_copy, may_share_bounds)
+from cupy_b200._core._reduction import ReductionKernel, create_reduction_func  # noqa: F401
+from cupy_b200._core._routines_math import (  # noqa: F401
+    add, subtract, multiply, true_divide, divide, negative, absolute, square, sqrt, exp, log,
+    expm1, exp2, log2, log10, log1p, sin, cos, tan, tanh, sinh, cosh, arctan2, hypot,
+    maximum, minimum, power, fma, greater, greater_equal, less, less_equal, equal, not_equal,
+    sum, prod, cumsum, cumprod)
+from cupy_b200._core._routines_statistics import (  # noqa: F401
+    amax, amin, argmax, argmin, mean, var, std)
+
+abs = absolute
+max = amax
+min = amin
+
+__version__ = '0.1.0'

@@ -1,0 +1,835 @@
+"""The elementwise engine: `ufunc`, `ElementwiseKernel` and the launcher.
+
+Host-side mirror of cupy/_core/_kernel.pyx -- same classes, argument meaning,
+defaults and error messages -- over the B200 C ABI:
+
+* `_broadcast_core`              cupy/_core/internal.pyx:320-376
+* `ParameterInfo`, `_get_param_info`, `_decide_params_type_core`
+                                 cupy/_core/_kernel.pyx:464-604
+* `ElementwiseKernel`            cupy/_core/_kernel.pyx:743-1002
+* `ufunc`, `_Op`, `_Ops`, `create_ufunc` (NEP-50 weak scalars)
+                                 cupy/_core/_kernel.pyx:1103-1766
+* overlap guard                  cupy/_core/_kernel.pyx:673-683, _memory_range.pyx
+
+What differs is below the call: instead of rendering a one-element-per-thread
+CUPY_FOR loop per (dtype, ndim, contiguity) (`_kernel.pyx:78-107`), the call is
+handed to `b200_ew_plan` (collapse dims + classify FLAT / ROWWISE / TILED), and
+either a prebuilt kernel is launched (`b200_ufunc_launch`) or the operation
+string is wrapped in the tiler glue of `_codegen.py` and compiled by NVRTC.
+"""
+from __future__ import annotations
+
+import ctypes
+import string
+import threading
+
+import numpy
+
+from cupy_b200 import _lib
+from cupy_b200._core import _codegen, _dryrun, _jit, _scalar
+from cupy_b200._core._ndarray import ndarray, current_stream_ptr
+from cupy_b200._core._scalar import CScalar, get_dtype, get_typename
+
+_thread_local = threading.local()
+
+
+# ---------------------------------------------------------------------------
+# argument preprocessing
+# ---------------------------------------------------------------------------
+def _convert_arg(arg):
+    if isinstance(arg, ndarray):
+        return arg
+    if hasattr(arg, '__cuda_array_interface__') or type(arg).__module__.startswith('torch'):
+        from cupy_b200._core import _ndarray
+        return _ndarray.asarray(arg)
+    return CScalar(arg)
+
+
+def _preprocess_args(args):
+    return [_convert_arg(a) for a in args]
+
+
+def _broadcast_core(arrays):
+    """Broadcast the ndarray entries of `arrays` in place; returns the shape."""
+    idx = [i for i, a in enumerate(arrays) if isinstance(a, ndarray)]
+    if not idx:
+        return ()
+    nd = max(arrays[i].ndim for i in idx)
+    shape = []
+    for d in range(nd):
+        s = 1
+        for i in idx:
+            a = arrays[i]
+            k = d - (nd - a.ndim)
+            if k < 0:
+                continue
+            a_sh = a.shape[k]
+            if a_sh == s or a_sh == 1:
+                continue
+            if s == 1:
+                s = a_sh
+                continue
+            raise ValueError(
+                'operands could not be broadcast together with shapes {}'.format(
+                    ' '.join([str(x.shape) if isinstance(x, ndarray) else '()' for x in arrays])))
+        shape.append(s)
+    shape = tuple(shape)
+    for i in idx:
+        a = arrays[i]
+        if a.shape != shape:
+            arrays[i] = a.broadcast_to(shape)
+    return shape
+
+
+def _get_bound(a):
+    left, right = 0, a.dtype.itemsize
+    for s, t in zip(a.shape, a.strides):
+        if s == 0:
+            return a.ptr, a.ptr
+        tmp = (s - 1) * t
+        if tmp > 0:
+            right += tmp
+        else:
+            left += tmp
+    return a.ptr + left, a.ptr + right
+
+
+def may_share_bounds(a, b):
+    if a.size == 0 or b.size == 0:
+        return False
+    al, ar = _get_bound(a)
+    bl, br = _get_bound(b)
+    return al < br and bl < ar
+
+
+def _copy_in_args_if_needed(in_args, out_args):
+    for i, a in enumerate(in_args):
+        if isinstance(a, ndarray):
+            for out in out_args:
+                if a is not out and may_share_bounds(a, out):
+                    in_args[i] = a.copy()
+                    break
+
+
+# ---------------------------------------------------------------------------
+# parameters of user kernels
+# ---------------------------------------------------------------------------
+class ParameterInfo:
+    __slots__ = ('name', 'dtype', 'ctype', 'raw', 'is_const')
+
+    def __init__(self, param, is_const):
+        self.name = None
+        self.dtype = None
+        self.ctype = None
+        self.raw = False
+        self.is_const = is_const
+        s = tuple(i for i in param.split() if len(i) != 0)
+        if len(s) < 2:
+            raise Exception('Syntax error: %s' % param)
+        t, self.name = s[-2:]
+        if t == 'CIndexer':
+            pass
+        elif len(t) == 1:
+            self.ctype = t
+        else:
+            self.dtype = get_dtype(t)
+            self.ctype = get_typename(self.dtype)
+        for i in s[:-2]:
+            if i == 'raw':
+                self.raw = True
+            elif i == '_non_const':
+                self.is_const = False
+            else:
+                raise Exception('Unknown keyword "%s"' % i)
+
+    def _key(self):
+        return (self.name, self.dtype, self.ctype, self.raw, self.is_const)
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __eq__(self, other):
+        return isinstance(other, ParameterInfo) and self._key() == other._key()
+
+    def __repr__(self):
+        return '<ParameterInfo name=%r dtype=%r ctype=%r raw=%r is_const=%r>' % self._key()
+
+
+_param_info_memo = {}
+
+
+def _get_param_info(s, is_const):
+    key = (s, is_const)
+    r = _param_info_memo.get(key)
+    if r is None:
+        r = () if len(s) == 0 else tuple(ParameterInfo(i, is_const) for i in s.strip().split(','))
+        _param_info_memo[key] = r
+    return r
+
+
+def _decide_params_type_core(in_params, out_params, in_args_dtype, out_args_dtype):
+    type_dict = {}
+    if out_args_dtype:
+        assert len(out_params) == len(out_args_dtype)
+        for p, a in zip(out_params, out_args_dtype):
+            if a is None:
+                raise TypeError('Output arguments must be cupy.ndarray')
+            if p.dtype is not None:
+                if get_dtype(a) != get_dtype(p.dtype):
+                    raise TypeError('Type is mismatched. %s %s %s' % (p.name, a, p.dtype))
+            elif p.ctype in type_dict:
+                t = type_dict[p.ctype]
+                if get_dtype(t) != get_dtype(a):
+                    raise TypeError('Type is mismatched. %s %s %s %s' % (p.name, a, t, p.ctype))
+            else:
+                type_dict[p.ctype] = a
+    assert len(in_params) == len(in_args_dtype)
+    for p, a in zip(in_params, in_args_dtype):
+        if a is None:
+            continue
+        if p.dtype is not None:
+            if numpy.dtype(a) != numpy.dtype(p.dtype):
+                raise TypeError('Type is mismatched. %s %s %s' % (p.name, a, p.dtype))
+        elif p.ctype in type_dict:
+            t = type_dict[p.ctype]
+            if numpy.dtype(t) != numpy.dtype(a):
+                raise TypeError('Type is mismatched. %s %s %s %s' % (p.name, a, t, p.ctype))
+        else:
+            type_dict[p.ctype] = a
+    try:
+        in_types = tuple(type_dict[p.ctype] if p.dtype is None else p.dtype for p in in_params)
+        out_types = tuple(type_dict[p.ctype] if p.dtype is None else p.dtype for p in out_params)
+    except KeyError as e:
+        raise TypeError('Type %s of a parameter could not be inferred from the arguments' % e)
+    type_map = tuple(sorted((k, get_dtype(v)) for k, v in type_dict.items()))
+    return in_types, out_types, type_map
+
+
+def _broadcast(args, params, use_size):
+    value = []
+    any_nonraw_array = False
+    for a, p in zip(args, params):
+        if not p.raw and isinstance(a, ndarray):
+            any_nonraw_array = True
+            value.append(a)
+        else:
+            value.append(None)
+    if use_size:
+        if any_nonraw_array:
+            raise ValueError('Specified \'size\' can be used only if all of the ndarray are \'raw\'.')
+    else:
+        if not any_nonraw_array:
+            raise ValueError('Loop size is undecided.')
+    shape = _broadcast_core(value)
+    for i, a in enumerate(value):
+        if a is None:
+            value[i] = args[i]
+    return value, shape
+
+
+def _get_out_args_from_optionals(out_args, out_types, out_shape, casting):
+    out_args = list(out_args)
+    while len(out_args) < len(out_types):
+        out_args.append(None)
+    for i, a in enumerate(out_args):
+        if a is None:
+            out_args[i] = ndarray(out_shape, out_types[i])
+            continue
+        if not isinstance(a, ndarray):
+            raise TypeError('Output arguments type must be cupy.ndarray')
+        if a.shape != tuple(out_shape):
+            raise ValueError('Out shape is mismatched')
+        _scalar.raise_if_invalid_cast(out_types[i], a.dtype, casting, 'output operand')
+    return out_args
+
+
+def _get_out_args_with_params(out_args, out_types, out_shape, out_params, is_size_specified):
+    if not out_args:
+        for p in out_params:
+            if p.raw and not is_size_specified:
+                raise ValueError('Output array size is Undecided')
+        return [ndarray(out_shape, t) for t in out_types]
+    for a, p in zip(out_args, out_params):
+        if not isinstance(a, ndarray):
+            raise TypeError('Output arguments type must be cupy.ndarray')
+        if not p.raw and a.shape != tuple(out_shape):
+            raise ValueError('Out shape is mismatched')
+    return list(out_args)
+
+
+# ---------------------------------------------------------------------------
+# the launcher
+# ---------------------------------------------------------------------------
+def _make_operands(args, params, n_in, loop_shape):
+    """args (ndarray | CScalar) -> C operand array.  Non-raw arrays must already
+    be broadcast to `loop_shape`."""
+    n = len(args)
+    if n > _lib.MAX_ARGS:
+        raise ValueError('too many kernel arguments (%d > %d)' % (n, _lib.MAX_ARGS))
+    ops = (_lib.Operand * n)()
+    for k, (a, p) in enumerate(zip(args, params)):
+        o = ops[k]
+        if isinstance(a, ndarray):
+            if a.ndim > _lib.MAX_NDIM:
+                a = _collapse_for_abi(a)
+            o.data = a.ptr
+            o.kind = _lib.KIND_RAW if p.raw else _lib.KIND_ARRAY
+            o.dtype = _scalar.dtype_id(a.dtype)
+            o.ndim = a.ndim
+            o.is_output = 1 if k >= n_in else 0
+            for d in range(a.ndim):
+                o.shape[d] = a.shape[d]
+                o.strides[d] = a.strides[d]
+        else:
+            o.kind = _lib.KIND_SCALAR
+            o.dtype = _scalar.dtype_id(a.descr)
+            raw = a.raw_bytes()
+            o.scalar[0] = int.from_bytes(raw[:8], 'little', signed=True)
+            o.scalar[1] = int.from_bytes(raw[8:16], 'little', signed=True)
+    return ops
+
+
+def _collapse_for_abi(a):
+    raise NotImplementedError('arrays with more than %d dimensions are not supported' % _lib.MAX_NDIM)
+
+
+def plan_elementwise(args, params, n_in, loop_shape):
+    ops = _make_operands(args, params, n_in, loop_shape)
+    plan = _lib.EwPlan()
+    if not any(o.kind == _lib.KIND_ARRAY for o in ops):
+        # all-raw kernel with explicit size: a 1-D loop of `size` elements
+        plan.variant = _lib.EW_FLAT
+        plan.ndim = 1
+        plan.vec = 1
+        plan.idx32 = 1 if _prod(loop_shape) < 2 ** 31 else 0
+        plan.nargs = len(args)
+        plan.size = _prod(loop_shape)
+        plan.shape[0] = plan.size
+        return ops, plan
+    _lib.check(_lib.lib.b200_ew_plan(len(args), ops, ctypes.byref(plan)))
+    return ops, plan
+
+
+def _prod(shape):
+    r = 1
+    for s in shape:
+        r *= int(s)
+    return r
+
+
+# tunables of the generated kernels (bench/tuning scripts override these)
+tunables = {
+    'threads': 256,
+    'flat_unroll': 4,
+    'row_unroll': 2,
+    'blocks_per_sm': 0,       # 0 = library default
+}
+
+
+def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stream=None):
+    """spec: _codegen.EwSpec describing parameters / operation strings."""
+    variant = plan.variant
+    threads = tunables['threads'] if block_size is None else int(block_size)
+    if variant == _lib.EW_TILED:
+        threads, unroll, vec = 256, 4, 1
+    elif variant == _lib.EW_FLAT:
+        unroll, vec = tunables['flat_unroll'], plan.vec
+    else:
+        unroll, vec = tunables['row_unroll'], plan.vec
+    arginfo = tuple(
+        ('raw', a.dtype.char, a.ndim, a._c_contiguous) if (isinstance(a, ndarray) and p.raw)
+        else ('arr', a.dtype.char) if isinstance(a, ndarray) else ('scalar', a.descr.char)
+        for a, p in zip(args, params))
+    key = (name, variant, vec, unroll, threads, bool(plan.idx32), plan.ndim if spec.uses_ind else -1, arginfo)
+    fn = spec.memo.get(key)
+    if fn is None:
+        source = _codegen.render_elementwise(
+            spec, name, args, params, variant=variant, vec=vec, unroll=unroll, threads=threads,
+            idx32=bool(plan.idx32), ndim=plan.ndim)
+        spec.last_source = source
+        fn = _jit.get_function(source, name, spec.options)
+        spec.memo[key] = fn
+    plan.reserved = (unroll & 0xff) | ((tunables['blocks_per_sm'] & 0xffff) << 8)
+    if _dryrun.enabled:
+        _dryrun.record('jit_elementwise', name=name, variant=variant, vec=vec, ndim=plan.ndim,
+                       idx32=bool(plan.idx32), staged_mask=plan.staged_mask, tile_axis=plan.tile_axis,
+                       shape=tuple(plan.shape[:plan.ndim]), source=spec.last_source)
+        return
+    st = current_stream_ptr() if stream is None else _stream_ptr(stream)
+    _lib.check(_lib.lib.b200_jit_ew_launch(fn.handle, ctypes.byref(plan), len(args), ops, threads, st))
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        return current_stream_ptr()
+    if isinstance(stream, int):
+        return stream
+    for attr in ('cuda_stream', 'ptr'):
+        if hasattr(stream, attr):
+            return int(getattr(stream, attr))
+    raise TypeError('unsupported stream object %r' % (stream,))
+
+
+# ---------------------------------------------------------------------------
+# ElementwiseKernel
+# ---------------------------------------------------------------------------
+class ElementwiseKernel:
+    """User-defined elementwise kernel (drop-in for cupy.ElementwiseKernel,
+    cupy/_core/_kernel.pyx:743-1002: same constructor, `__call__(*args, size=,
+    stream=, block_size=)`, same errors)."""
+
+    def __init__(self, in_params, out_params, operation, name='kernel', reduce_dims=True,
+                 preamble='', no_return=False, return_tuple=False, **kwargs):
+        if not _jit.is_valid_kernel_name(name):
+            raise ValueError('Invalid kernel name: "%s"' % name)
+        self.in_params = _get_param_info(in_params, True)
+        self.out_params = _get_param_info(out_params, False)
+        self.nin = len(self.in_params)
+        self.nout = len(self.out_params)
+        self.nargs = self.nin + self.nout
+        self.params = self.in_params + self.out_params
+        self.operation = operation
+        self.name = name
+        self.__name__ = name
+        self.reduce_dims = reduce_dims
+        self.preamble = preamble
+        self.no_return = no_return
+        self.return_tuple = return_tuple
+        self.kwargs = kwargs
+        bad = set(kwargs) - {'options', 'loop_prep', 'after_loop'}
+        if bad:
+            raise TypeError('Wrong arguments %s' % {k: kwargs[k] for k in bad})
+        names = [p.name for p in self.params]
+        if 'i' in names:
+            raise ValueError('Can not use \'i\' as a parameter name')
+        self._params_type_memo = {}
+        self._cached_codes = {}
+        self._spec = _codegen.EwSpec(
+            mode='elementwise', operation=operation, preamble=preamble,
+            loop_prep=kwargs.get('loop_prep', ''), after_loop=kwargs.get('after_loop', ''),
+            options=tuple(kwargs.get('options', ())))
+
+    def __call__(self, *args, **kwargs):
+        size = kwargs.pop('size', -1)
+        stream = kwargs.pop('stream', None)
+        block_size = kwargs.pop('block_size', 128)
+        if len(kwargs):
+            raise TypeError('Wrong arguments %s' % kwargs)
+        if block_size <= 0:
+            raise ValueError('block_size must be greater than zero')
+        n_args = len(args)
+        if n_args != self.nin and n_args != self.nargs:
+            raise TypeError(
+                'Wrong number of arguments for {!r}. It must be either {} or {} (with outputs), '
+                'but given {}.'.format(self.name, self.nin, self.nargs, n_args))
+        for arg in args:
+            if hasattr(arg, '__cupy_override_elementwise_kernel__'):
+                return arg.__cupy_override_elementwise_kernel__(self, *args, **kwargs)
+        arg_list = _preprocess_args(args)
+        out_args = arg_list[self.nin:]
+        bcast, shape = _broadcast(arg_list, self.params, size != -1)
+        in_args = bcast[:self.nin]
+
+        in_ndarray_types = tuple(a.dtype if isinstance(a, ndarray) else None for a in in_args)
+        out_ndarray_types = tuple(a.dtype if isinstance(a, ndarray) else None for a in out_args)
+        in_types, out_types, type_map = self._decide_params_type(in_ndarray_types, out_ndarray_types)
+
+        is_size_specified = False
+        if size != -1:
+            shape = (int(size),)
+            is_size_specified = True
+        out_args = _get_out_args_with_params(out_args, out_types, shape, self.out_params, is_size_specified)
+        if self.no_return:
+            ret = None
+        elif not self.return_tuple and self.nout == 1:
+            ret = out_args[0]
+        else:
+            ret = tuple(out_args)
+        if 0 in shape:
+            return ret
+
+        for i, x in enumerate(in_args):
+            if isinstance(x, CScalar):
+                x.apply_dtype(in_types[i])
+        inout_args = in_args + out_args
+        ops, plan = plan_elementwise(inout_args, self.params, self.nin, shape)
+        # the 128-thread default of the reference is a floor for its scalar loop;
+        # the tilers are built for 256 -- a caller's explicit block_size is honoured
+        bs = None if block_size == 128 else block_size
+        self._spec.type_map = type_map
+        _launch_jit(self.name, self._spec.bind(type_map), inout_args, self.params, self.nin, ops, plan,
+                    block_size=bs, stream=stream)
+        key = tuple(t for t in in_ndarray_types if t is not None)
+        if key not in self._cached_codes:
+            self._cached_codes[key] = self._spec.bind(type_map).last_source
+        return ret
+
+    def _decide_params_type(self, in_args_dtype, out_args_dtype):
+        key = (in_args_dtype, out_args_dtype)
+        ret = self._params_type_memo.get(key)
+        if ret is None:
+            ret = _decide_params_type_core(self.in_params, self.out_params, in_args_dtype, out_args_dtype)
+            self._params_type_memo[key] = ret
+        return ret
+
+    @property
+    def cached_codes(self):
+        if len(self._cached_codes) == 0:
+            import warnings
+            warnings.warn('No codes are cached because compilation is deferred until the first function call.')
+        return dict(self._cached_codes.items())
+
+    @property
+    def cached_code(self):
+        codes = self._cached_codes
+        if len(codes) > 1:
+            import warnings
+            warnings.warn('The input types of the kernel could not be inferred. Please use `.cached_codes` instead.')
+        return next(iter(codes.values()))
+
+
+# ---------------------------------------------------------------------------
+# ufunc
+# ---------------------------------------------------------------------------
+def _get_kind_score(kind):
+    if issubclass(kind, (numpy.bool_, bool)):
+        return 0
+    if issubclass(kind, (numpy.integer, int)):
+        return 1
+    if issubclass(kind, (numpy.inexact, float, complex)):
+        return 2
+    return 3
+
+
+def _check_should_use_weak_scalar(in_types, weaks):
+    """cupy/_core/_kernel.pyx:1114-1144."""
+    if weaks is None:
+        return False
+    max_array_kind = -1
+    max_scalar_kind = -1
+    for in_t, w_t in zip(in_types, weaks):
+        if w_t:
+            max_scalar_kind = max(max_scalar_kind, _get_kind_score(w_t))
+        else:
+            max_array_kind = max(max_array_kind, _get_kind_score(in_t.type))
+    all_scalars_or_arrays = max_scalar_kind == -1 or max_array_kind == -1
+    return not all_scalars_or_arrays and max_array_kind >= max_scalar_kind
+
+
+class _Op:
+    def __init__(self, in_types, out_types, routine, error_func):
+        self.in_types = tuple(get_dtype(t) for t in in_types)
+        self.out_types = tuple(get_dtype(t) for t in out_types)
+        self.nin = len(in_types)
+        self.nout = len(out_types)
+        self.routine = routine
+        self.error_func = error_func
+
+    @staticmethod
+    def from_type(typ, routine, error_func=None):
+        types = typ.split('->')
+        if len(types) == 1:
+            in_types = out_types = tuple(types)
+        else:
+            in_types, out_types = map(tuple, types)
+        return _Op(in_types, out_types, routine, error_func)
+
+    def check_valid(self):
+        if self.error_func is not None:
+            self.error_func()
+
+    def __repr__(self):
+        return '_Op(%s->%s)' % (''.join(t.char for t in self.in_types), ''.join(t.char for t in self.out_types))
+
+
+class _Ops:
+    def __init__(self, ops):
+        assert len(ops) > 0
+        self.ops = tuple(ops)
+        self.nin = ops[0].nin
+        self.nout = ops[0].nout
+        for op in ops:
+            if op.nin != self.nin or op.nout != self.nout:
+                raise ValueError('invalid op %s, wrong nin or nout.' % op)
+
+    @staticmethod
+    def from_tuples(ops, routine):
+        ops_ = []
+        for t in ops:
+            if isinstance(t, tuple):
+                typ, rt = t
+                if rt is None:
+                    rt = routine
+                elif isinstance(rt, tuple):
+                    rt = tuple(r1 or r2 for r1, r2 in zip(rt, routine))
+                elif not isinstance(rt, str):
+                    assert callable(rt)
+                    ops_.append(_Op.from_type(typ, None, rt))
+                    continue
+            else:
+                typ, rt = t, routine
+            ops_.append(_Op.from_type(typ, rt))
+        return _Ops(ops_)
+
+    def guess_routine(self, name, cache, in_args, dtype, out_ops):
+        if dtype is None:
+            in_types, weaks, any_weak = [], [], False
+            for a in in_args:
+                if isinstance(a, CScalar):
+                    t, w = a.descr, a.weak_t
+                    if w is not False:
+                        any_weak = True
+                elif isinstance(a, ndarray):
+                    t, w = a.dtype, False
+                else:
+                    raise RuntimeError('Need array or CScalar got %s' % type(a))
+                in_types.append(t)
+                weaks.append(w)
+            in_types = tuple(in_types)
+            weaks = tuple(weaks) if any_weak else None
+            if not _check_should_use_weak_scalar(in_types, weaks):
+                weaks = (False,) * len(in_args)
+            op = cache.get((in_types, weaks), ())
+            if op == ():
+                op = self._guess_routine_from_in_types(in_types, weaks)
+                cache[(in_types, weaks)] = op
+        else:
+            op = cache.get(dtype, ())
+            if op == ():
+                op = (out_ops or self)._guess_routine_from_dtype(dtype)
+                cache[dtype] = op
+        if op is not None:
+            op.check_valid()
+            return op
+        if dtype is None:
+            dtype = in_types
+        raise TypeError('Wrong type (%s) of arguments for %s' % (dtype, name))
+
+    def _guess_routine_from_in_types(self, in_types, weaks=None):
+        for op in self.ops:
+            for i in range(self.nin):
+                it, ot = in_types[i], op.in_types[i]
+                weak_t = weaks[i] if weaks is not None else False
+                if not numpy.can_cast(it, ot):
+                    if not weak_t:
+                        break
+                    try:
+                        if numpy.result_type(weak_t(0), ot) != ot:
+                            break
+                    except TypeError:
+                        break
+            else:
+                return op
+        return None
+
+    def _guess_routine_from_dtype(self, dtype):
+        for op in self.ops:
+            if all(t == dtype for t in op.out_types):
+                return op
+        return None
+
+
+class ufunc:
+    """Universal function (drop-in for cupy.ufunc, cupy/_core/_kernel.pyx:1147-1493)."""
+
+    def __init__(self, name, nin, nout, ops, preamble='', loop_prep='', doc='',
+                 default_casting=None, out_ops=None, prebuilt=None):
+        self.name = name
+        self.__name__ = name
+        self.nin = nin
+        self.nout = nout
+        self.nargs = nin + nout
+        self._ops = ops
+        self._out_ops = out_ops
+        self._preamble = preamble
+        self._loop_prep = loop_prep
+        self.__doc__ = doc
+        self._default_casting = 'same_kind' if default_casting is None else default_casting
+        self._prebuilt = _lib.UFUNC_IDS.get(prebuilt) if prebuilt else None
+        self._params = tuple(ParameterInfo('T in%d' % i, True) for i in range(nin)) + \
+            tuple(ParameterInfo('T out%d' % i, False) for i in range(nout))
+        self._params_with_where = self._params[:nin] + (ParameterInfo('T _where', True),) + self._params[nin:]
+        self._routine_cache = {}
+        self._specs = {}
+
+    def __repr__(self):
+        return '<ufunc \'%s\'>' % self.name
+
+    @property
+    def types(self):
+        return ['%s->%s' % (''.join(t.char for t in op.in_types), ''.join(t.char for t in op.out_types))
+                for op in self._ops.ops]
+
+    def __call__(self, *args, **kwargs):
+        for arg in args:
+            if hasattr(arg, '__cupy_override_elementwise_kernel__'):
+                return arg.__cupy_override_elementwise_kernel__(self, *args, **kwargs)
+        fusing = getattr(_thread_local, 'fusion', None)
+        if fusing is not None:
+            return fusing.call_ufunc(self, *args, **kwargs)
+
+        out = kwargs.pop('out', None)
+        where = kwargs.pop('_where', None)
+        has_where = where is not None
+        dtype = kwargs.pop('dtype', None)
+        casting = kwargs.pop('casting', self._default_casting)
+        if dtype is not None:
+            dtype = get_dtype(dtype)
+        if kwargs:
+            raise TypeError('Wrong arguments %s' % kwargs)
+        n_args = len(args)
+        if not (self.nin <= n_args <= self.nargs):
+            raise TypeError(
+                'Wrong number of arguments for {!r}. It must be either {} or {} (with outputs), '
+                'but given {}.'.format(self.name, self.nin, self.nargs, n_args))
+        in_args = args[:self.nin]
+        out_args = args[self.nin:]
+        if out is not None:
+            if out_args:
+                raise ValueError('Cannot specify \'out\' as both a positional and keyword argument')
+            if isinstance(out, tuple):
+                if len(out) != self.nout:
+                    raise ValueError("The 'out' tuple must have exactly one entry per ufunc output")
+                out_args = out
+            else:
+                if 1 != self.nout:
+                    raise ValueError("'out' must be a tuple of arrays")
+                out_args = (out,)
+        in_args = _preprocess_args(in_args)
+        out_args = [None if o is None else _convert_arg(o) for o in out_args]
+        given_out_args = [o for o in out_args if o is not None]
+
+        if has_where:
+            w = _convert_arg(where)
+            if isinstance(w, ndarray):
+                if w.dtype != numpy.bool_:
+                    raise TypeError('Cannot cast array data from %r to %r according to the rule \'safe\''
+                                    % (w.dtype, numpy.dtype(bool)))
+            else:
+                w = CScalar(bool(w.value))
+            where_args = [w]
+        else:
+            where_args = []
+
+        _copy_in_args_if_needed(in_args, given_out_args)
+        _copy_in_args_if_needed(where_args, given_out_args)
+        inout_args = in_args + where_args + given_out_args
+        shape = _broadcast_core(inout_args)
+        in_args = inout_args[:self.nin]
+        where_args = inout_args[self.nin:self.nin + len(where_args)]
+
+        op = self._ops.guess_routine(self.name, self._routine_cache, in_args, dtype, self._out_ops)
+        out_args = _get_out_args_from_optionals(out_args, op.out_types, shape, casting)
+        ret = out_args[0] if self.nout == 1 else tuple(out_args)
+        if 0 in shape:
+            return ret
+        for i, t in enumerate(op.in_types):
+            if isinstance(in_args[i], CScalar):
+                in_args[i].apply_dtype(t)
+
+        all_args = in_args + where_args + out_args
+        params = self._params_with_where if has_where else self._params
+        n_in = self.nin + len(where_args)
+        ops, plan = plan_elementwise(all_args, params, n_in, shape)
+        st = current_stream_ptr()
+
+        # ---- prebuilt kernel?
+        if (self._prebuilt is not None and not has_where and self.nout == 1
+                and all(a.dtype == t if isinstance(a, ndarray) else True for a, t in zip(in_args, op.in_types))
+                and (self._prebuilt == 0 or out_args[0].dtype == op.out_types[0])):
+            in_ids = (ctypes.c_int32 * self.nin)(*[_scalar.dtype_id(t) for t in op.in_types])
+            if self._prebuilt == 0:   # copy: keyed by the memory dtypes
+                in_ids[0] = _scalar.dtype_id(in_args[0].dtype if isinstance(in_args[0], ndarray) else op.in_types[0])
+            if _lib.lib.b200_ufunc_supported(self._prebuilt, self.nin, in_ids, _scalar.dtype_id(out_args[0].dtype)):
+                if _dryrun.enabled:
+                    _dryrun.record('prebuilt_ufunc', name=self.name, variant=plan.variant, vec=plan.vec,
+                                   ndim=plan.ndim, idx32=bool(plan.idx32), staged_mask=plan.staged_mask,
+                                   tile_axis=plan.tile_axis, shape=tuple(plan.shape[:plan.ndim]))
+                    return ret
+                _lib.check(_lib.lib.b200_ufunc_launch(self._prebuilt, ctypes.byref(plan), len(all_args), ops, st))
+                return ret
+
+        # ---- NVRTC route: the routine string inside the same tiler glue
+        spec = self._get_spec(op, has_where)
+        _launch_jit(self._kernel_name(all_args, has_where), spec, all_args, params, n_in, ops, plan)
+        return ret
+
+    def _get_spec(self, op, has_where):
+        key = (op, has_where)
+        spec = self._specs.get(key)
+        if spec is None:
+            spec = _codegen.EwSpec(
+                mode='ufunc', operation=op.routine, preamble=self._preamble, loop_prep=self._loop_prep,
+                after_loop='', options=(), in_types=op.in_types, out_types=op.out_types, has_where=has_where)
+            self._specs[key] = spec
+        return spec
+
+    def _kernel_name(self, args, has_where):
+        name = self.name + ('_where' if has_where else '')
+        words = []
+        for a in args:
+            if isinstance(a, ndarray):
+                words.append(a.dtype.name)
+            else:
+                words.append(a.descr.name.rstrip('0123456789'))
+        return '{}__{}'.format(name, '_'.join(words))
+
+    def outer(self, A, B, **kwargs):
+        from cupy_b200._core import _ndarray
+        A = _ndarray.asarray(A)
+        B = _ndarray.asarray(B)
+        A = A.reshape(A.shape + (1,) * B.ndim)
+        B = B.reshape((1,) * (A.ndim - B.ndim) + B.shape) if B.ndim else B
+        return self(A, B, **kwargs)
+
+    def at(self, a, indices, b=None):
+        raise NotImplementedError('`%s.at` is not supported yet' % self.name)
+
+    def reduce(self, array, axis=0, dtype=None, out=None, keepdims=False):
+        if self.name == 'cupy_add':
+            return array.sum(axis, dtype, out, keepdims)
+        if self.name == 'cupy_multiply':
+            return array.prod(axis, dtype, out, keepdims)
+        raise NotImplementedError('`%s.reduce` is not supported yet' % self.name)
+
+    def accumulate(self, array, axis=0, dtype=None, out=None):
+        if self.name == 'cupy_add':
+            return array.cumsum(axis, dtype, out)
+        if self.name == 'cupy_multiply':
+            return array.cumprod(axis, dtype, out)
+        raise NotImplementedError('`%s.accumulate` is not supported yet' % self.name)
+
+    def reduceat(self, array, indices, axis=0, dtype=None, out=None):
+        raise NotImplementedError('`%s.reduceat` is not supported yet' % self.name)
+
+
+def create_ufunc(name, ops, routine=None, preamble='', doc='', default_casting=None,
+                 loop_prep='', out_ops=None, prebuilt=None):
+    ops_ = _Ops.from_tuples(ops, routine)
+    _out_ops = None if out_ops is None else _Ops.from_tuples(out_ops, routine)
+    return ufunc(name, ops_.nin, ops_.nout, ops_, preamble, loop_prep, doc,
+                 default_casting=default_casting, out_ops=_out_ops, prebuilt=prebuilt)
+
+
+# ---------------------------------------------------------------------------
+# elementwise_copy (cupy/_core/_ufuncs.py:7-13) and helpers built on the engine
+# ---------------------------------------------------------------------------
+_copy_ufunc = create_ufunc(
+    'cupy_copy',
+    ('?->?', 'b->b', 'B->B', 'h->h', 'H->H', 'i->i', 'I->I', 'l->l', 'L->L',
+     'q->q', 'Q->Q', 'e->e', 'f->f', 'd->d'),
+    'out0 = in0', default_casting='unsafe', prebuilt='copy')
+
+
+def elementwise_copy(src, dst):
+    """dst[...] = src with dtype cast (`astype`, `copy`, `fill`, `out=` handling)."""
+    return _copy_ufunc(src, dst)
+
+
+_arange_memo = []
+
+
+def _arange_kernel():
+    if not _arange_memo:
+        _arange_memo.append(ElementwiseKernel('T start, T step', 'T y', 'y = start + step * i', 'cupy_arange'))
+    return _arange_memo[0]

@@ -19,7 +19,7 @@ from __future__ import annotations
 import numpy
 import torch
 
-from cupy_b200._core import _scalar
+from cupy_b200._core import _dryrun, _scalar
 
 _TORCH_DTYPES = {
     numpy.dtype('bool'): torch.bool, numpy.dtype('int8'): torch.int8,
@@ -44,6 +44,8 @@ except Exception:  # pragma: no cover
 
 
 def current_stream_ptr():
+    if _dryrun.enabled:
+        return 0
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -139,8 +141,12 @@ class ndarray:
         self._strides = tuple(int(s) for s in strides)
         if memptr is None:
             nbytes = max(self.size * itemsize, 1)
-            self._mem = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
-            self.ptr = self._mem.data_ptr()
+            if _dryrun.enabled:
+                self._mem = None
+                self.ptr = _dryrun.fake_alloc(nbytes)
+            else:
+                self._mem = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+                self.ptr = self._mem.data_ptr()
         else:
             self._mem = _mem
             self.ptr = int(memptr)
@@ -649,23 +655,17 @@ def asnumpy(a, stream=None, order='C', out=None):
 
 
 def from_torch(t):
+    """Zero-copy view of a CUDA torch.Tensor (the tensor's storage is kept alive)."""
     if not t.is_cuda:
         raise ValueError('from_torch needs a CUDA tensor (cupy_b200 has no CPU arrays)')
     dt = _NUMPY_DTYPES.get(t.dtype)
     if dt is None:
         raise TypeError('Unsupported torch dtype %s' % t.dtype)
     isz = dt.itemsize
+    st = t.untyped_storage()
+    mem = torch.empty(0, dtype=torch.uint8, device=t.device).set_(st, 0, (st.nbytes(),), (1,))
     return ndarray(tuple(t.shape), dt, memptr=t.data_ptr(),
-                   strides=tuple(s * isz for s in t.stride()), _mem=t.untyped_storage_owner()
-                   if hasattr(t, 'untyped_storage_owner') else _TorchOwner(t))
-
-
-class _TorchOwner:
-    """Keeps a foreign torch tensor alive and exposes a uint8 alias of its storage."""
-
-    def __new__(cls, t):
-        st = t.untyped_storage()
-        return torch.empty(0, dtype=torch.uint8, device=t.device).set_(st, 0, (st.nbytes(),), (1,))
+                   strides=tuple(s * isz for s in t.stride()), _mem=mem)
 
 
 def from_cuda_array_interface(obj):

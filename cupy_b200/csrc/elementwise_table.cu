@@ -13,56 +13,62 @@
 namespace b200 {
 
 
-template <class Tiler, class F>
-__global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ EwParams p) {
+template <bool FULL, class Tiler, class F>
+__device__ __forceinline__ void ew_tile(const Tiler& t, const EwParams& p) {
     constexpr int V = Tiler::kV, U = Tiler::kU;
     typedef typename F::in0_t T0;
     typedef typename F::in1_t T1;
     typedef typename F::in2_t T2;
     typedef typename F::out_t TO;
-    Tiler t(p);
-    for (; t.valid(); t.next()) {
-        Pack<T0, V> a0[U];
-        Pack<T1, V> a1[U];
-        Pack<T2, V> a2[U];
-        Pack<TO, V> o[U];
-        if (p.scalar_mask & 1u) {
-            const T0 s = scalar_arg<T0>(p, 0);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int k = 0; k < V; ++k) a0[u][k] = s;
-        } else {
-            t.load(0, a0);
-        }
-        if (F::nin >= 2) {
-            if (p.scalar_mask & 2u) {
-                const T1 s = scalar_arg<T1>(p, 1);
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int k = 0; k < V; ++k) a1[u][k] = s;
-            } else {
-                t.load(1, a1);
-            }
-        }
-        if (F::nin >= 3) {
-            if (p.scalar_mask & 4u) {
-                const T2 s = scalar_arg<T2>(p, 2);
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int k = 0; k < V; ++k) a2[u][k] = s;
-            } else {
-                t.load(2, a2);
-            }
-        }
+    Pack<T0, V> a0[U];
+    Pack<T1, V> a1[U];
+    Pack<T2, V> a2[U];
+    Pack<TO, V> o[U];
+    if (p.scalar_mask & 1u) {
+        const T0 s = scalar_arg<T0>(p, 0);
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int k = 0; k < V; ++k)
-                o[u][k] = F::apply(a0[u][k], F::nin >= 2 ? a1[u][k] : T1(), F::nin >= 3 ? a2[u][k] : T2());
-        t.store(F::nin, o);
+            for (int k = 0; k < V; ++k) a0[u][k] = s;
+    } else {
+        t.template load<FULL>(0, a0);
+    }
+    if (F::nin >= 2) {
+        if (p.scalar_mask & 2u) {
+            const T1 s = scalar_arg<T1>(p, 1);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < V; ++k) a1[u][k] = s;
+        } else {
+            t.template load<FULL>(1, a1);
+        }
+    }
+    if (F::nin >= 3) {
+        if (p.scalar_mask & 4u) {
+            const T2 s = scalar_arg<T2>(p, 2);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < V; ++k) a2[u][k] = s;
+        } else {
+            t.template load<FULL>(2, a2);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            o[u][k] = F::apply(a0[u][k], F::nin >= 2 ? a1[u][k] : T1(), F::nin >= 3 ? a2[u][k] : T2());
+    t.template store<FULL>(F::nin, o);
+}
+
+template <class Tiler, class F>
+__global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ EwParams p) {
+    Tiler t(p);
+    for (; t.valid(); t.next()) {
+        if (t.is_full()) ew_tile<true, Tiler, F>(t, p);
+        else ew_tile<false, Tiler, F>(t, p);
     }
 }
 

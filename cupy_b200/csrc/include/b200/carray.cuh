@@ -18,6 +18,9 @@ struct RawView {
     int64_t strides[kMaxNdim];   // bytes
 };
 
+// up to four `raw` operands per kernel, passed as the second kernel parameter
+struct RawPack { RawView v[4]; };
+
 }  // namespace b200
 
 // The template signature mirrors the reference so user preambles that spell the

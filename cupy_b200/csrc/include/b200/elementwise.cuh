@@ -7,12 +7,12 @@
 // same for all three:
 //
 //     Tiler t(p);
-//     for (; t.valid(); t.next()) {
-//         Pack<T0,V> a[U]; t.load(0, a);  ...            // inputs
-//         Pack<TO,V> o[U];                                // outputs
-//         for u, k:  if (t.in_range(u,k)) { i = t.index(u,k); o[u][k] = f(a[u][k]...); }
-//         t.store(NIN, o);
-//     }
+//     for (; t.valid(); t.next())            // FULL = the tile lies wholly inside the array:
+//         tile<FULL = t.is_full()>:          // no predicates, no tail code on that path
+//             Pack<T0,V> a[U]; t.load<FULL>(0, a);  ...            // inputs
+//             Pack<TO,V> o[U];                                      // outputs
+//             for u, k:  if (t.in_range<FULL>(u,k)) { i = t.index(u,k); o[u][k] = f(a[u][k]...); }
+//             t.store<FULL>(NIN, o);
 //
 // Replaces the reference's one-element-per-thread CUPY_FOR loop
 // (cupy/_core/_kernel.pyx:86-97, cupy/_core/include/cupy/carray.cuh:68-72) and
@@ -41,6 +41,9 @@ struct EwParams {
     FastDiv  fdiv[kMaxNdim];       // fast division by shape[d] (valid when size < 2^31)
     EwArg    arg[kMaxArgs];
 };
+
+struct true_t { static constexpr bool value = true; };
+struct false_t { static constexpr bool value = false; };
 
 template <class T>
 B200_DEVICE T scalar_arg(const EwParams& p, int a) {
@@ -74,12 +77,14 @@ struct FlatTiler {
     B200_DEVICE int64_t index(int u, int k) const {
         return base + (int64_t(u) * THREADS + threadIdx.x) * VEC + k;
     }
-    B200_DEVICE bool in_range(int u, int k) const { return full || index(u, k) < p.size; }
+    B200_DEVICE bool is_full() const { return full; }
+    template <bool FULL>
+    B200_DEVICE bool in_range(int u, int k) const { return FULL || index(u, k) < p.size; }
 
-    template <class T>
+    template <bool FULL, class T>
     B200_DEVICE void load(int a, Pack<T, VEC> (&r)[UNROLL]) const {
         const T* __restrict__ ptr = reinterpret_cast<const T*>(p.arg[a].ptr);
-        if (full) {
+        if (FULL) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) load_pack(r[u], ptr + index(u, 0));
         } else {
@@ -96,10 +101,10 @@ struct FlatTiler {
             }
         }
     }
-    template <class T>
+    template <bool FULL, class T>
     B200_DEVICE void store(int a, const Pack<T, VEC> (&r)[UNROLL]) const {
         T* __restrict__ ptr = reinterpret_cast<T*>(p.arg[a].ptr);
-        if (full) {
+        if (FULL) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) store_pack(ptr + index(u, 0), r[u]);
         } else {
@@ -198,16 +203,16 @@ struct RowTiler {
         locate();
     }
     B200_DEVICE int64_t index(int u, int k) const { return lin[u] + k; }
-    B200_DEVICE bool in_range(int u, int k) const {
-        return ok[u];
-    }
+    B200_DEVICE bool is_full() const { return wbase + int64_t(THREADS) * UNROLL <= total; }
+    template <bool FULL>
+    B200_DEVICE bool in_range(int u, int) const { return FULL || ok[u]; }
 
-    template <class T>
+    template <bool FULL, class T>
     B200_DEVICE void load(int a, Pack<T, VEC> (&r)[UNROLL]) const {
         const int64_t si = p.arg[a].strides[p.ndim - 1];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            if (!ok[u]) continue;
+            if (!FULL && !ok[u]) continue;
             const char* base = p.arg[a].ptr + off[u][a];
             if (VEC > 1 && si == int64_t(sizeof(T))) {
                 load_pack(r[u], reinterpret_cast<const T*>(base));
@@ -217,24 +222,22 @@ struct RowTiler {
                 for (int k = 0; k < VEC; ++k) r[u][k] = v;
             } else {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k)
-                    if (in_range(u, k)) r[u][k] = *reinterpret_cast<const T*>(base + k * si);
+                for (int k = 0; k < VEC; ++k) r[u][k] = *reinterpret_cast<const T*>(base + k * si);
             }
         }
     }
-    template <class T>
+    template <bool FULL, class T>
     B200_DEVICE void store(int a, const Pack<T, VEC> (&r)[UNROLL]) const {
         const int64_t si = p.arg[a].strides[p.ndim - 1];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            if (!ok[u]) continue;
+            if (!FULL && !ok[u]) continue;
             char* base = p.arg[a].ptr + off[u][a];
             if (VEC > 1 && si == int64_t(sizeof(T))) {
                 store_pack(reinterpret_cast<T*>(base), r[u]);
             } else {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k)
-                    if (in_range(u, k)) *reinterpret_cast<T*>(base + k * si) = r[u][k];
+                for (int k = 0; k < VEC; ++k) *reinterpret_cast<T*>(base + k * si) = r[u][k];
             }
         }
     }
@@ -291,13 +294,15 @@ struct TileTiler {
     }
     B200_DEVICE bool valid() const { return live; }
     B200_DEVICE void next() { live = false; }
+    B200_DEVICE bool is_full() const { return i0 + kTile <= n_i && o0 + kTile <= n_o; }
     // compute-phase ownership: element (i = i0 + ty + 8u, o = o0 + tx)
-    B200_DEVICE bool in_range(int u, int) const { return (i0 + ty + 8 * u) < n_i && (o0 + tx) < n_o; }
+    template <bool FULL>
+    B200_DEVICE bool in_range(int u, int) const { return FULL || ((i0 + ty + 8 * u) < n_i && (o0 + tx) < n_o); }
     B200_DEVICE int64_t index(int u, int) const {
         return lin0 + (i0 + ty + 8 * u) * p.cstride[p.tile_axis] + (o0 + tx);
     }
 
-    template <class T>
+    template <bool FULL, class T>
     B200_DEVICE void load(int a, Pack<T, 1> (&r)[4]) const {
         const int64_t s_i = p.arg[a].strides[p.tile_axis];
         const int64_t s_o = p.arg[a].strides[p.ndim - 1];
@@ -308,7 +313,7 @@ struct TileTiler {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int64_t o = o0 + ty + 8 * u, i = i0 + tx;
-                if (o < n_o && i < n_i)
+                if (FULL || (o < n_o && i < n_i))
                     tile[ty + 8 * u][tx] = *reinterpret_cast<const W*>(base + i * s_i + o * s_o);
             }
             __syncthreads();
@@ -321,18 +326,18 @@ struct TileTiler {
         } else {
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (in_range(u, 0))
+                if (in_range<FULL>(u, 0))
                     r[u][0] = *reinterpret_cast<const T*>(base + (i0 + ty + 8 * u) * s_i + (o0 + tx) * s_o);
         }
     }
-    template <class T>
+    template <bool FULL, class T>
     B200_DEVICE void store(int a, const Pack<T, 1> (&r)[4]) const {
         const int64_t s_i = p.arg[a].strides[p.tile_axis];
         const int64_t s_o = p.arg[a].strides[p.ndim - 1];
         char* base = p.arg[a].ptr + boff[a];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (in_range(u, 0))
+            if (in_range<FULL>(u, 0))
                 *reinterpret_cast<T*>(base + (i0 + ty + 8 * u) * s_i + (o0 + tx) * s_o) = r[u][0];
     }
 };

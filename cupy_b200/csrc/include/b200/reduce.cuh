@@ -27,11 +27,12 @@ namespace b200 {
 
 template <class T>
 B200_DEVICE T load_volatile(const T* p) {
-    constexpr int words = sizeof(T) / 4;
-    static_assert(sizeof(T) % 4 == 0, "accumulators are shuffled/copied in 32-bit words");
-    union U { T t; uint32_t w[words]; B200_DEVICE U() {} };
+    // accumulators published by other blocks: read around L1, in words when possible
+    typedef typename RawVec<(sizeof(T) % 4 == 0) ? 4 : 1>::type W;
+    constexpr int words = sizeof(T) / sizeof(W);
+    union U { T t; W w[words]; B200_DEVICE U() {} };
     U u;
-    const volatile uint32_t* s = reinterpret_cast<const volatile uint32_t*>(p);
+    const volatile W* s = reinterpret_cast<const volatile W*>(p);
 #pragma unroll
     for (int i = 0; i < words; ++i) u.w[i] = s[i];
     return u.t;
@@ -74,7 +75,9 @@ __device__ __forceinline__ void reduce_full_body(
     typedef typename Op::acc_t acc_t;
     typedef typename Op::index_t index_t;
     constexpr int64_t kTile = int64_t(THREADS) * VEC * UNROLL;
-    __shared__ acc_t smem[THREADS / 32];
+    // raw storage: acc_t may have user constructors (the reference's min_max_st)
+    __shared__ __align__(16) char smem_raw[(THREADS / 32) * sizeof(acc_t)];
+    acc_t* smem = reinterpret_cast<acc_t*>(smem_raw);
     __shared__ bool is_last;
 
     acc_t acc[UNROLL][VEC];
@@ -142,7 +145,9 @@ __device__ __forceinline__ void reduce_rows_body(
     typedef typename Op::index_t index_t;
     constexpr int kRowsPerBlock = THREADS / GROUP;
     constexpr int64_t kTile = int64_t(GROUP) * VEC * UNROLL;
-    __shared__ acc_t smem[THREADS / 32];
+    // raw storage: acc_t may have user constructors (the reference's min_max_st)
+    __shared__ __align__(16) char smem_raw[(THREADS / 32) * sizeof(acc_t)];
+    acc_t* smem = reinterpret_cast<acc_t*>(smem_raw);
     const int g = threadIdx.x % GROUP;       // lane within the row group
     const int gi = threadIdx.x / GROUP;      // which row of the block
 
@@ -203,7 +208,8 @@ __device__ __forceinline__ void reduce_cols_body(
     typedef typename Op::index_t index_t;
     constexpr int kWarps = 8;
     constexpr int kTileCols = 32 * VEC;
-    __shared__ acc_t smem[kWarps][kTileCols];
+    __shared__ __align__(16) char smem_raw[kWarps * kTileCols * sizeof(acc_t)];
+    acc_t (*smem)[kTileCols] = reinterpret_cast<acc_t (*)[kTileCols]>(smem_raw);
     __shared__ bool is_last;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -281,6 +287,85 @@ __device__ __forceinline__ void reduce_cols_body(
         y[b * cols + tile_c0 + t] = op.post(a, n);
     }
     if (threadIdx.x == 0) tickets[b * gridDim.x + blockIdx.x] = 0u;
+}
+
+// ---------------------------------------------------------------------------
+// GENERIC: any strides, any number of (broadcast) inputs and outputs -- the
+// fallback for layouts that are none of FULL / ROWS / COLS and for user
+// ReductionKernels with several array operands (e.g. the reference's
+// _var_core kernels: x, broadcast mean, alpha).  GROUP threads per output
+// element; every element's offsets come from an index decomposition, so this
+// is correct for everything and fast for nothing in particular.
+// The functor provides map_at / post_at, which read / write through pointers.
+// ---------------------------------------------------------------------------
+template <int NIN, int NOUT>
+struct GenericReduceParams {
+    int32_t out_ndim, red_ndim;
+    int64_t out_size, red_size;
+    int64_t out_shape[kMaxNdim], red_shape[kMaxNdim];
+    int64_t in_out_strides[NIN][kMaxNdim];    // input strides along the out dims (bytes)
+    int64_t in_red_strides[NIN][kMaxNdim];    // input strides along the reduced dims
+    int64_t out_strides[NOUT][kMaxNdim];
+    char*   in_ptr[NIN];
+    char*   out_ptr[NOUT];
+};
+
+template <class Op, int NIN, int NOUT, int THREADS, int GROUP>
+__device__ __forceinline__ void reduce_generic_body(const Op& op, const GenericReduceParams<NIN, NOUT>& p) {
+    typedef typename Op::acc_t acc_t;
+    typedef typename Op::index_t index_t;
+    constexpr int kPerBlock = THREADS / GROUP;
+    // raw storage: acc_t may have user constructors (the reference's min_max_st)
+    __shared__ __align__(16) char smem_raw[(THREADS / 32) * sizeof(acc_t)];
+    acc_t* smem = reinterpret_cast<acc_t*>(smem_raw);
+    const int g = threadIdx.x % GROUP, gi = threadIdx.x / GROUP;
+
+    for (int64_t o0 = int64_t(blockIdx.x) * kPerBlock; o0 < p.out_size; o0 += int64_t(gridDim.x) * kPerBlock) {
+        const int64_t o = o0 + gi;
+        const bool live = o < p.out_size;
+        const char* ibase[NIN];
+        char* obase[NOUT];
+#pragma unroll
+        for (int a = 0; a < NIN; ++a) ibase[a] = p.in_ptr[a];
+#pragma unroll
+        for (int a = 0; a < NOUT; ++a) obase[a] = p.out_ptr[a];
+        if (live) {
+            int64_t rest = o;
+#pragma unroll 1
+            for (int d = p.out_ndim - 1; d >= 0; --d) {
+                const int64_t q = rest / p.out_shape[d], r = rest - q * p.out_shape[d];
+                rest = q;
+#pragma unroll
+                for (int a = 0; a < NIN; ++a) ibase[a] += r * p.in_out_strides[a][d];
+#pragma unroll
+                for (int a = 0; a < NOUT; ++a) obase[a] += r * p.out_strides[a][d];
+            }
+        }
+        acc_t acc = op.identity();
+        if (live) {
+            for (int64_t j = g; j < p.red_size; j += GROUP) {
+                const char* ptrs[NIN];
+#pragma unroll
+                for (int a = 0; a < NIN; ++a) ptrs[a] = ibase[a];
+                int64_t rest = j;
+#pragma unroll 1
+                for (int d = p.red_ndim - 1; d >= 0; --d) {
+                    const int64_t q = rest / p.red_shape[d], r = rest - q * p.red_shape[d];
+                    rest = q;
+#pragma unroll
+                    for (int a = 0; a < NIN; ++a) ptrs[a] += r * p.in_red_strides[a][d];
+                }
+                acc = op.combine(acc, op.map_at(ptrs, static_cast<index_t>(j)));
+            }
+        }
+        if (GROUP == THREADS) {
+            acc = block_combine(op, acc, smem);
+            if (threadIdx.x == 0) op.post_at(obase, acc);
+        } else {
+            if (GROUP > 1) acc = group_combine<(GROUP > 32 ? 32 : GROUP)>(op, acc);
+            if (g == 0 && live) op.post_at(obase, acc);
+        }
+    }
 }
 
 }  // namespace b200

@@ -111,8 +111,6 @@ static int cu_fail(Driver* d, CUresult r, const char* what) {
     return fail(int(r), "%s: %s", what, msg ? msg : "CUDA driver error");
 }
 
-struct RawPack { RawView v[4]; };
-
 }  // namespace b200
 
 using namespace b200;
@@ -236,7 +234,7 @@ extern "C" __attribute__((visibility("default"))) int b200_jit_ew_launch(void* f
     if (st) return st;
     // block_size: threads per block the kernel was generated for; unroll is
     // encoded by the generator in the plan's reserved field
-    const int unroll = plan->reserved ? int(plan->reserved) : 1;
+    const int unroll = (plan->reserved & 0xff) ? int(plan->reserved & 0xff) : 1;
     const int threads = plan->variant == B200_EW_TILED ? 256 : block_size;
     const unsigned grid = ew_grid(plan, threads, unroll, di.sm_count);
     void* kargs[] = {&p, &raws};

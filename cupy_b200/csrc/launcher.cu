@@ -99,8 +99,10 @@ unsigned ew_grid(const b200_ew_plan_t* plan, int threads, int unroll, int sm_cou
     const int64_t work = plan->size / std::max(1, plan->vec);          // vectors
     const int64_t per_block = int64_t(threads) * unroll;
     blocks = (work + per_block - 1) / per_block;
-    // persistent: enough resident blocks to cover HBM latency, then grid-stride
-    const int64_t cap = int64_t(sm_count) * (2048 / threads) * 4;
+    // persistent: enough resident blocks to cover HBM latency, then grid-stride.
+    // plan->reserved bits 8..23: blocks per SM override (tuning sweeps)
+    const int per_sm = ((plan->reserved >> 8) & 0xffff) ? int((plan->reserved >> 8) & 0xffff) : (2048 / threads) * 4;
+    const int64_t cap = int64_t(sm_count) * per_sm;
     return unsigned(std::max<int64_t>(1, std::min(blocks, cap)));
 }
 

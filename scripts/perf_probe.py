@@ -1,0 +1,109 @@
+"""Device-timed GB/s of the configs in BASELINE.json (development probe; bench.py is the contract)."""
+import sys, json
+import numpy as np
+sys.path.insert(0, '.')
+import torch
+import cupy_b200 as cp
+from cupy_b200._core import _kernel
+
+PEAK = 6545.9
+
+
+def timeit(f, iters=20, warm=3):
+    for _ in range(warm):
+        f()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        f()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(iters)]
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def report(name, nbytes, f, **kw):
+    try:
+        med, mn = timeit(f, **kw)
+        print('%-44s %9.3f ms (min %8.3f)  %8.1f GB/s  %5.1f%% of measured peak' % (
+            name, med, mn, nbytes / med / 1e6, 100 * nbytes / med / 1e6 / PEAK), flush=True)
+    except Exception as e:
+        print('%-44s ERROR %s: %s' % (name, type(e).__name__, str(e)[:300]), flush=True)
+
+
+def randn(shape, dtype):
+    t = torch.rand(shape, device='cuda', dtype=torch.float32) * 2 - 1
+    return t.to(dtype)
+
+
+def main():
+    which = sys.argv[1:] or ['copy', 'axpy', 'sum', 'c3', 'c4', 'scan']
+    n = 1 << 28
+    if 'copy' in which:
+        a = torch.empty(n, device='cuda', dtype=torch.float32); b = torch.empty_like(a)
+        report('torch copy_ f32 2^28 (R+W)', 8 * n, lambda: b.copy_(a))
+        report('torch sum f32 2^28', 4 * n, lambda: a.sum())
+        del a, b
+    if 'axpy' in which:
+        x = cp.from_torch(randn((n,), torch.float32)); y = cp.from_torch(randn((n,), torch.float32))
+        z = cp.empty((n,), np.float32)
+        k = cp.ElementwiseKernel('T a, T x, T y', 'T z', 'z = a * x + y', 'axpy')
+        a = np.float32(1.5)
+        report('axpy ElementwiseKernel 2^28 (JIT)', 12 * n, lambda: k(a, x, y, z))
+        for unroll in (1, 2, 8):
+            _kernel.tunables['flat_unroll'] = unroll
+            report('  axpy unroll=%d' % unroll, 12 * n, lambda: k(a, x, y, z))
+        _kernel.tunables['flat_unroll'] = 4
+        for bps in (8, 16, 64, 4096):
+            _kernel.tunables['blocks_per_sm'] = bps
+            report('  axpy blocks/SM=%d' % bps, 12 * n, lambda: k(a, x, y, z))
+        _kernel.tunables['blocks_per_sm'] = 0
+        report('x*2 prebuilt 2^28', 8 * n, lambda: cp.multiply(x, 2, out=z))
+        report('x+y prebuilt 2^28', 12 * n, lambda: cp.add(x, y, out=z))
+        report('fma prebuilt 2^28', 16 * n, lambda: cp.fma(x, y, z, out=z))
+        report('exp prebuilt 2^28', 8 * n, lambda: cp.exp(x, out=z))
+        del x, y, z
+    if 'sum' in which:
+        x = cp.from_torch(randn((n,), torch.float32))
+        report('sum f32 2^28 (full)', 4 * n, lambda: x.sum())
+        report('max f32 2^28 (full)', 4 * n, lambda: x.max())
+        report('argmax f32 2^28 (full)', 4 * n, lambda: x.argmax())
+        report('var f32 2^28 (full)', 4 * n, lambda: x.var())
+        del x
+    if 'c3' in which:
+        for dt, tdt in ((np.float32, torch.float32), (np.float16, torch.float16)):
+            m = 32768
+            x = cp.from_torch(randn((m, m), tdt))
+            nb = m * m * np.dtype(dt).itemsize
+            for op in ('sum', 'max', 'argmax', 'var'):
+                for ax in (0, 1):
+                    report('%s axis=%d %s 32768^2' % (op, ax, np.dtype(dt).name), nb,
+                           lambda: getattr(x, op)(axis=ax), iters=10)
+            del x
+            torch.cuda.empty_cache()
+    if 'c4' in which:
+        base = cp.from_torch(randn((256, 1024, 1024), torch.float32))
+        xt = base.transpose(2, 1, 0)       # shape (1024,1024,256), strides (4, 4096, 4194304)
+        v = cp.from_torch(randn((256,), torch.float32))
+        out = cp.empty((1024, 1024, 256), np.float32)
+        tmp = cp.empty((1024, 1024, 256), np.float32)
+        nel = 1 << 28
+        report('exp(x^T) transposed -> contiguous', 8 * nel, lambda: cp.exp(xt, out=tmp), iters=10)
+        report('tmp + v (broadcast row)', 8 * nel, lambda: cp.add(tmp, v, out=out), iters=10)
+        fused = cp.ElementwiseKernel('T x, T v', 'T z', 'z = exp(x) + v', 'expadd')
+        report('fused exp(x^T)+v ElementwiseKernel', 8 * nel, lambda: fused(xt, v, out), iters=10)
+        report('copy transposed (ascontiguous)', 8 * nel, lambda: cp.elementwise_copy(xt, out), iters=10)
+        del base, xt, out, tmp
+        torch.cuda.empty_cache()
+    if 'scan' in which:
+        xi = cp.from_torch(torch.randint(-(1 << 20), 1 << 20, (n,), device='cuda', dtype=torch.int64))
+        yo = cp.empty((n,), np.int64)
+        report('cumsum int64 2^28', 16 * n, lambda: cp.cumsum(xi, out=yo), iters=10)
+        xf = cp.from_torch(randn((n,), torch.float32)); yf = cp.empty((n,), np.float32)
+        report('cumsum f32 2^28', 8 * n, lambda: cp.cumsum(xf, out=yf), iters=10)
+        report('torch cumsum int64 2^28', 16 * n, lambda: torch.cumsum(xi.to_torch(), 0), iters=5)
+
+
+if __name__ == '__main__':
+    main()
