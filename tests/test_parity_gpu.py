@@ -1,0 +1,437 @@
+"""GPU tier: parity of the CUDA path with the CPU oracle, through the public surface
+(which calls the C ABI).  Bars (BASELINE.json north_star): bit-exact for integer work,
+argmax indices, scans and IEEE-exact ufuncs; <= 2 ulp for transcendentals; relative 1e-5
+(float32) / float16-rounding for float reductions whose summation order differs."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import ref_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def cp():
+    import cupy_b200
+    return cupy_b200
+
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'hotpath_v1.npz'))
+RS = np.random.RandomState(7)
+
+
+def rnd(shape, dt):
+    dt = np.dtype(dt)
+    if dt.kind == 'f':
+        return (RS.rand(*shape) * 2 - 1).astype(dt)
+    if dt.kind == 'b':
+        return RS.rand(*shape) > 0.5
+    if dt.kind == 'u':
+        return RS.randint(0, 200, size=shape).astype(dt)
+    return RS.randint(-100, 100, size=shape).astype(dt)
+
+
+def tol_sum(a, axis, dt):
+    """Float reduction tolerance: rtol 1e-5 of the sum of magnitudes (order-independent bound)."""
+    mag = np.abs(a.astype(np.float64)).sum(axis=axis)
+    eps = {2: 1e-3, 4: 1e-5, 8: 1e-13}[np.dtype(dt).itemsize]
+    return eps * np.maximum(mag, 1e-30)
+
+
+# ---------------------------------------------------------------------------------------------
+# 1. the reference's own known-answer tests, run through the CUDA path
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', ref_cases.KNOWN_ANSWERS, ids=[c[0] for c in ref_cases.KNOWN_ANSWERS])
+def test_reference_known_answers(cp, case):
+    cid, ref, build, op, kwargs, expect = case
+    a = build()
+    d = cp.asarray(a)
+    assert d.shape == a.shape and d.strides == a.strides
+    if op == 'cumsum_same_dtype':
+        got = cp.cumsum(d, dtype=None if a.dtype == np.bool_ else a.dtype).get()
+        want = oracle.cumsum(a, dtype=None if a.dtype == np.bool_ else a.dtype)
+    else:
+        got = getattr(d, op)(**kwargs).get()
+        want = {'argmax': oracle.argmax, 'argmin': oracle.argmin, 'max': oracle.amax, 'min': oracle.amin,
+                'sum': oracle.sum, 'mean': oracle.mean, 'var': oracle.var}[op](a, **kwargs)
+    assert got.dtype == want.dtype and got.shape == want.shape, (cid, got.dtype, want.dtype, got.shape, want.shape)
+    if want.dtype.kind in 'iub' or op in ('max', 'min'):
+        np.testing.assert_array_equal(got, want, err_msg='%s (%s)' % (cid, ref))
+    else:
+        np.testing.assert_allclose(got.astype(np.float64), want.astype(np.float64),
+                                   rtol=2e-3 if want.dtype == np.float16 else 1e-6, err_msg='%s (%s)' % (cid, ref))
+    if expect is not None and not (isinstance(expect, float) and np.isnan(expect)):
+        np.testing.assert_allclose(got.astype(np.float64), np.asarray(expect, np.float64),
+                                   rtol=2e-3 if a.dtype == np.float16 else 1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# 2. golden vectors (one small instance of every BASELINE.json config)
+# ---------------------------------------------------------------------------------------------
+def test_golden_axpy_bit_exact(cp):
+    k = cp.ElementwiseKernel('T a, T x, T y', 'T z', 'z = a * x + y', 'axpy')
+    z = k(G['axpy_a'][()], cp.asarray(G['axpy_x']), cp.asarray(G['axpy_y']))
+    np.testing.assert_array_equal(z.get(), G['axpy_z'])
+    np.testing.assert_array_equal((cp.asarray(G['axpy_x']) * 2 + 1).get(), G['affine_z'])
+    np.testing.assert_array_equal(cp.fma(cp.asarray(G['axpy_x']), np.float32(1.5), cp.asarray(G['axpy_y'])).get(),
+                                  oracle.axpy(1.5, G['axpy_x'], G['axpy_y']))
+
+
+def test_golden_axis_reductions(cp):
+    for name, arr in (('f32', G['red_a']), ('f16', G['red_h'])):
+        d = cp.asarray(arr)
+        for ax in (0, 1):
+            got = d.sum(axis=ax).get()
+            want = G['sum_%s_ax%d' % (name, ax)]
+            assert got.dtype == want.dtype
+            if name == 'f16':
+                assert oracle.ulp_diff(got, want).max() <= 1            # fp32 accumulate, one rounding to half
+            else:
+                assert (np.abs(got.astype(np.float64) - want) <= tol_sum(arr, ax, arr.dtype)).all()
+            np.testing.assert_array_equal(d.max(axis=ax).get(), G['max_%s_ax%d' % (name, ax)])
+            np.testing.assert_array_equal(d.argmax(axis=ax).get(), G['argmax_%s_ax%d' % (name, ax)])
+            gv, wv = d.var(axis=ax).get(), G['var_%s_ax%d' % (name, ax)]
+            assert gv.dtype == wv.dtype
+            np.testing.assert_allclose(gv.astype(np.float64), wv.astype(np.float64), rtol=2e-3 if name == 'f16' else 1e-5)
+
+
+def test_golden_exp_transposed_broadcast(cp):
+    t, v = cp.asarray(G['exp_t']), cp.asarray(G['exp_v'])
+    xt = t.transpose(2, 1, 0)
+    two = cp.exp(xt) + v                                                     # two launches (ufuncs)
+    fused = cp.ElementwiseKernel('T x, T v', 'T z', 'z = exp(x) + v', 'exp_add')(xt, v)   # one launch
+    e = np.exp(G['exp_t'].transpose(2, 1, 0).astype(np.float64))
+    bound = 2 * np.spacing(e.astype(np.float32)) + np.spacing(np.abs(G['exp_z']))          # 2 ulp of exp + final rounding
+    for got in (two.get(), fused.get()):
+        assert got.flags.c_contiguous and got.shape == G['exp_z'].shape
+        assert (np.abs(got.astype(np.float64) - (e + G['exp_v'])) <= bound).all()
+    assert oracle.ulp_diff(cp.exp(xt).get(), oracle.exp_exact(G['exp_t'].transpose(2, 1, 0))).max() <= 2
+
+
+def test_golden_scan_bit_exact(cp):
+    np.testing.assert_array_equal(cp.cumsum(cp.asarray(G['scan_x'])).get(), G['scan_y'])
+
+
+# ---------------------------------------------------------------------------------------------
+# 3. elementwise engine: dtype x layout sweeps
+# ---------------------------------------------------------------------------------------------
+LAYOUTS = {
+    'flat': lambda a: a,
+    'transposed': lambda a: a.T,
+    'strided': lambda a: a[::2, 1::3],
+    'reversed': lambda a: a[::-1],
+    'row': lambda a: a[3:4],
+    'col': lambda a: a[:, 5:6],
+    'sliced_misaligned': lambda a: a[:, 1:],
+}
+
+
+@pytest.mark.parametrize('dt', ['int8', 'uint8', 'int16', 'int32', 'int64', 'uint64', 'float16', 'float32', 'float64'])
+@pytest.mark.parametrize('layout', sorted(LAYOUTS))
+def test_binary_ufuncs_match_numpy(cp, dt, layout):
+    a, b = rnd((70, 130), dt), rnd((70, 130), dt)
+    va, vb = LAYOUTS[layout](a), LAYOUTS['flat' if layout in ('row', 'col') else layout](b)
+    da, db = LAYOUTS[layout](cp.asarray(a)), LAYOUTS['flat' if layout in ('row', 'col') else layout](cp.asarray(b))
+    for name in ('add', 'subtract', 'multiply', 'maximum', 'minimum'):
+        got = getattr(cp, name)(da, db).get()
+        with np.errstate(over='ignore'):
+            want = getattr(np, name)(va, vb)
+        assert got.dtype == want.dtype and got.shape == want.shape
+        np.testing.assert_array_equal(got, want, err_msg=name)          # IEEE-exact / integer-exact
+
+
+@pytest.mark.parametrize('dt', ['float16', 'float32', 'float64'])
+def test_transcendentals_within_2ulp(cp, dt):
+    a = rnd((257, 129), dt) * 8
+    d = cp.asarray(a)
+    for name, dom in (('exp', a), ('log', np.abs(a) + 0.1), ('sqrt', np.abs(a)), ('tanh', a), ('sin', a)):
+        got = getattr(cp, name)(cp.asarray(dom.astype(dt))).get()
+        want = getattr(np, name)(dom.astype(dt).astype(np.float64)).astype(dt)
+        assert got.dtype == np.dtype(dt)
+        assert oracle.ulp_diff(got, want).max() <= (2 if name != 'sqrt' else 0), name
+    got = cp.true_divide(d, cp.asarray((np.abs(a) + 1).astype(dt))).get()
+    want = (a.astype(np.float64) / (np.abs(a) + 1).astype(dt).astype(np.float64)).astype(dt)
+    assert oracle.ulp_diff(got, want).max() <= (1 if dt == 'float16' else 0)
+
+
+def test_mixed_dtypes_scalars_where_and_casts(cp):
+    ai, af = rnd((33, 65), 'int32'), rnd((33, 65), 'float32')
+    di, df = cp.asarray(ai), cp.asarray(af)
+    np.testing.assert_array_equal((di + df).get(), ai + af)                  # -> float64 loop
+    np.testing.assert_array_equal((di * 3).get(), ai * 3)
+    np.testing.assert_array_equal((df * 2.5).get(), af * 2.5)
+    np.testing.assert_array_equal((di / 4).get(), ai / 4)
+    np.testing.assert_array_equal((2 - df).get(), 2 - af)
+    np.testing.assert_array_equal((-di).get(), -ai)
+    np.testing.assert_array_equal(abs(df).get(), abs(af))
+    np.testing.assert_array_equal(cp.power(di, 2).get(), np.power(ai, 2))
+    np.testing.assert_array_equal((di > 3).get(), ai > 3)
+    m = rnd((33, 65), '?')
+    out = cp.asarray(af.copy())
+    cp.add(df, df, out=out, _where=cp.asarray(m))
+    np.testing.assert_array_equal(out.get(), np.where(m, af + af, af))
+    for src, dst in (('float32', 'float16'), ('float32', 'int32'), ('int64', 'float32'), ('float64', 'int8'),
+                     ('int8', 'float16'), ('uint8', 'int64'), ('?', 'float32'), ('float16', '?')):
+        a = rnd((31, 17), src) * (50 if np.dtype(src).kind == 'f' else 1)
+        np.testing.assert_array_equal(cp.asarray(a).astype(dst).get(), a.astype(dst), err_msg='%s->%s' % (src, dst))
+    f = cp.asarray(np.asfortranarray(af))
+    assert f.flags.f_contiguous and (f + f).get().shape == af.shape
+    np.testing.assert_array_equal((f + df).get(), af + af)
+
+
+def test_broadcasting_shapes(cp):
+    a = rnd((6, 1, 40), 'float32')
+    b = rnd((5, 1), 'float32')
+    c = rnd((40,), 'float32')
+    np.testing.assert_array_equal((cp.asarray(a) + cp.asarray(b)).get(), a + b)
+    np.testing.assert_array_equal((cp.asarray(a) * cp.asarray(c)).get(), a * c)
+    np.testing.assert_array_equal((cp.asarray(b) - cp.asarray(c)).get(), b - c)
+    np.testing.assert_array_equal(cp.add.outer(cp.asarray(c), cp.asarray(c)).get(), np.add.outer(c, c))
+    z = rnd((), 'float32')
+    np.testing.assert_array_equal((cp.asarray(a) + cp.asarray(z)).get(), a + z)
+
+
+@pytest.mark.parametrize('shape,perm', [((64, 48, 40), (2, 1, 0)), ((64, 48, 40), (1, 0, 2)), ((64, 48, 40), (0, 2, 1)),
+                                        ((33, 65), (1, 0)), ((5, 6, 7, 8), (3, 1, 2, 0)), ((1025, 1023), (1, 0))])
+@pytest.mark.parametrize('dt', ['float32', 'float16', 'int64', 'int8'])
+def test_transposed_copies_and_ops(cp, shape, perm, dt):
+    a = rnd(shape, dt)
+    d = cp.asarray(a)
+    np.testing.assert_array_equal(d.transpose(perm).copy().get(), a.transpose(perm))
+    np.testing.assert_array_equal((d.transpose(perm) + d.transpose(perm)).get(), a.transpose(perm) + a.transpose(perm))
+    out = cp.empty(shape, dt).transpose(perm)                               # transposed OUTPUT
+    cp.add(d.transpose(perm), 0, out=out)
+    np.testing.assert_array_equal(out.get(), a.transpose(perm))
+
+
+def test_inplace_and_overlap(cp):
+    a = rnd((1000,), 'float32')
+    d = cp.asarray(a)
+    d += d
+    np.testing.assert_array_equal(d.get(), a + a)
+    d = cp.asarray(a)
+    o = d[1:]
+    cp.add(d[:-1], o, out=o)                                                # overlapping in/out: guarded by a copy
+    np.testing.assert_array_equal(d.get()[1:], a[:-1] + a[1:])
+    sq = cp.asarray(rnd((64, 64), 'float32'))
+    ref = sq.get()
+    cp.add(sq.T, 0, out=sq)                                                 # in-place transpose through the guard
+    np.testing.assert_array_equal(sq.get(), ref.T)
+
+
+# ---------------------------------------------------------------------------------------------
+# 4. user kernels (NVRTC into the skeleton)
+# ---------------------------------------------------------------------------------------------
+def test_elementwise_kernel_features(cp):
+    x = rnd((50, 60), 'float32')
+    d = cp.asarray(x)
+    # in-out parameter: the output is read
+    acc = cp.ElementwiseKernel('T x', 'T y', 'y += x', 'accum')
+    y0 = rnd((50, 60), 'float32')
+    dy = cp.asarray(y0)
+    acc(d, dy)
+    np.testing.assert_array_equal(dy.get(), y0 + x)
+    # conditional write keeps old contents; works on every layout
+    cond = cp.ElementwiseKernel('T x', 'T y', 'if (x > 0) y = x', 'condw')
+    for lay in ('flat', 'transposed', 'strided'):
+        dy = cp.asarray(y0)
+        cond(LAYOUTS[lay](d), LAYOUTS[lay](dy))
+        np.testing.assert_array_equal(dy.get(), _cond_expect(x, y0, lay))
+    # raw + i + _ind.size(), scalars, several outputs, preamble / loop_prep
+    k = cp.ElementwiseKernel('raw T x, int32 n', 'T y, int64 j', 'y = x[n - 1 - i] * scale(); j = i + _ind.size() - q',
+                             'multi', preamble='__device__ float scale() { return 2.f; }', loop_prep='long long q = 0')
+    y, j = k(cp.asarray(x.ravel()), x.size, size=x.size)
+    np.testing.assert_array_equal(y.get(), x.ravel()[::-1] * 2)
+    np.testing.assert_array_equal(j.get(), np.arange(x.size) + x.size)
+    # N-D raw indexing by index array and i on a broadcast, non-collapsible loop
+    k2 = cp.ElementwiseKernel('T a, T b', 'int64 lin', 'lin = i', 'lin_index')
+    got = k2(cp.asarray(x[:, :1]), cp.asarray(x[:1, :])).get()
+    np.testing.assert_array_equal(got, np.arange(x.size).reshape(x.shape))
+    # float16 arithmetic goes through float
+    h = rnd((777,), 'float16')
+    hk = cp.ElementwiseKernel('T x, T y', 'T z', 'z = x * y + x', 'half_op')
+    np.testing.assert_array_equal(hk(cp.asarray(h), cp.asarray(h)).get(),
+                                  (np.float32(h) * np.float32(h) + np.float32(h)).astype(np.float16))
+    # explicit stream / block_size
+    import torch
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        z = acc(d, cp.asarray(y0), stream=s, block_size=64)
+    s.synchronize()
+    np.testing.assert_array_equal(z.get(), y0 + x)
+
+
+def _cond_expect(x, y0, lay):
+    y = y0.copy()
+    vx, vy = LAYOUTS[lay](x), LAYOUTS[lay](y)
+    vy[...] = np.where(vx > 0, vx, vy)
+    return y
+
+
+def test_reduction_kernel_features(cp):
+    a = rnd((37, 53, 61), 'float32')
+    d = cp.asarray(a)
+    l2 = cp.ReductionKernel('T x', 'T y', 'x * x', 'a + b', 'y = sqrt(a)', '0', 'l2norm')
+    for ax in (0, 1, 2, (0, 2), None):
+        got = l2(d, axis=ax).get()
+        want = np.sqrt((a.astype(np.float64) ** 2).sum(axis=ax)).astype(np.float32)
+        np.testing.assert_allclose(got, want, rtol=1e-5)
+    dot = cp.ReductionKernel('T x, T y', 'T z', 'x * y', 'a + b', 'z = a', '0', 'dot')
+    b = rnd((53, 61), 'float32')
+    np.testing.assert_allclose(dot(d, cp.asarray(b), axis=(1, 2)).get(), (a.astype(np.float64) * b).sum(axis=(1, 2)),
+                               rtol=1e-4)
+    sc = cp.ReductionKernel('T x, float64 s', 'float64 z', 'x * s', 'a + b', 'z = a', '0', 'scaled', reduce_type='double')
+    np.testing.assert_allclose(sc(d, 0.5, axis=1).get(), a.astype(np.float64).sum(axis=1) * 0.5, rtol=1e-12)
+    cnt = cp.ReductionKernel('T x', 'int64 z', 'x > 0 ? 1 : 0', 'a + b', 'z = a', '0', 'count_pos', reduce_type='long long')
+    np.testing.assert_array_equal(cnt(d, axis=0).get(), (a > 0).sum(axis=0))
+    assert cnt(d, axis=0, keepdims=True).shape == (1, 53, 61)
+    out = cp.empty((37, 61), np.int64)
+    cnt(d, out, axis=1)
+    np.testing.assert_array_equal(out.get(), (a > 0).sum(axis=1))
+
+
+# ---------------------------------------------------------------------------------------------
+# 5. reductions: dtype x shape x axis x order sweeps (tests/cupy_tests/math_tests/test_sumprod.py,
+#    core_tests/test_reduction.py, statistics_tests/test_meanvar.py, sorting_tests/test_search.py)
+# ---------------------------------------------------------------------------------------------
+RED_SHAPES = [(1, 1), (1, 257), (257, 1), (3, 4), (127, 129), (517, 1031), (2049, 33), (5, 4099), (64, 8192)]
+
+
+@pytest.mark.parametrize('dt', ['?', 'int8', 'uint8', 'int16', 'int32', 'int64', 'float16', 'float32', 'float64'])
+@pytest.mark.parametrize('shape', RED_SHAPES)
+@pytest.mark.parametrize('order', ['C', 'F'])
+def test_reductions_sweep(cp, dt, shape, order):
+    a = np.asarray(rnd(shape, dt), order=order)
+    d = cp.asarray(a)
+    assert d.strides == a.strides
+    for ax in (0, 1, None):
+        got, want = d.sum(axis=ax).get(), oracle.sum(a, axis=ax)
+        assert got.dtype == want.dtype and got.shape == want.shape
+        if want.dtype.kind in 'iu':
+            np.testing.assert_array_equal(got, want)
+        elif dt == 'float16':
+            exact32 = a.astype(np.float64).sum(axis=ax)
+            assert (np.abs(got.astype(np.float64) - exact32) <= 1e-3 * np.maximum(np.abs(exact32), 1) + tol_sum(a, ax, 'float32')).all()
+        else:
+            assert (np.abs(got.astype(np.float64) - a.astype(np.float64).sum(axis=ax)) <= tol_sum(a, ax, dt)).all()
+        np.testing.assert_array_equal(d.max(axis=ax).get(), oracle.amax(a, axis=ax))
+        np.testing.assert_array_equal(d.min(axis=ax).get(), oracle.amin(a, axis=ax))
+        np.testing.assert_array_equal(d.argmax(axis=ax).get(), oracle.argmax(a, axis=ax))
+        np.testing.assert_array_equal(d.argmin(axis=ax).get(), oracle.argmin(a, axis=ax))
+        if dt != '?':
+            gm, wm = d.mean(axis=ax).get(), oracle.mean(a, axis=ax)
+            assert gm.dtype == wm.dtype
+            np.testing.assert_allclose(gm.astype(np.float64), wm.astype(np.float64),
+                                       rtol=2e-3 if dt == 'float16' else 1e-5, atol=1e-3 if dt == 'float16' else 1e-6)
+            gv, wv = d.var(axis=ax).get(), oracle.var(a, axis=ax)
+            assert gv.dtype == wv.dtype
+            np.testing.assert_allclose(gv.astype(np.float64), wv.astype(np.float64),
+                                       rtol=4e-3 if dt == 'float16' else 2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('dt', ['int32', 'float32', 'float16'])
+def test_reductions_nd_axes_keepdims_out(cp, dt):
+    a = rnd((7, 9, 11, 13), dt)
+    d = cp.asarray(a)
+    for ax in (0, 1, 2, 3, (0, 1), (2, 3), (1, 2), (0, 3), (0, 2), (1, 3), (0, 1, 2), (1, 2, 3), (0, 1, 2, 3), -1, (-1, 0)):
+        for keep in (False, True):
+            got, want = d.sum(axis=ax, keepdims=keep).get(), oracle.sum(a, axis=ax, keepdims=keep)
+            assert got.shape == want.shape and got.dtype == want.dtype
+            np.testing.assert_allclose(got.astype(np.float64), want.astype(np.float64), rtol=3e-3 if dt == 'float16' else 1e-5,
+                                       atol=0.05 if dt == 'float16' else 1e-4)
+            np.testing.assert_array_equal(d.max(axis=ax, keepdims=keep).get(), oracle.amax(a, axis=ax, keepdims=keep))
+        if not isinstance(ax, tuple):
+            np.testing.assert_array_equal(d.argmax(axis=ax).get(), oracle.argmax(a, axis=ax))
+    # non-contiguous inputs, out= (contiguous / strided / other dtype), dtype=
+    v = d.transpose(2, 0, 3, 1)[::2, :, 1:]
+    nv = a.transpose(2, 0, 3, 1)[::2, :, 1:]
+    np.testing.assert_allclose(v.sum(axis=1).get().astype(np.float64), oracle.sum(nv, axis=1).astype(np.float64),
+                               rtol=3e-3 if dt == 'float16' else 1e-5, atol=0.05 if dt == 'float16' else 1e-4)
+    np.testing.assert_array_equal(v.argmax(axis=2).get(), oracle.argmax(nv, axis=2))
+    np.testing.assert_array_equal(v.argmax().get(), oracle.argmax(nv))
+    out = cp.empty((7, 11, 13), np.float64)
+    r = d.sum(axis=1, out=out)
+    assert r is out
+    np.testing.assert_allclose(out.get(), a.astype(np.float64).sum(axis=1), rtol=1e-3 if dt == 'float16' else 1e-6, atol=1e-2)
+    big = cp.empty((7, 22, 13), oracle.sum_dtype(dt))
+    sl = big[:, ::2]
+    d.sum(axis=1, out=sl)
+    np.testing.assert_allclose(sl.get().astype(np.float64), oracle.sum(a, axis=1).astype(np.float64),
+                               rtol=3e-3 if dt == 'float16' else 1e-5, atol=0.05 if dt == 'float16' else 1e-4)
+    np.testing.assert_allclose(d.sum(axis=(0, 2), dtype=np.float64).get(), a.astype(np.float64).sum(axis=(0, 2)), rtol=1e-12)
+    np.testing.assert_allclose(d.prod(axis=3).get().astype(np.float64), oracle.prod(a, axis=3).astype(np.float64),
+                               rtol=5e-3 if dt == 'float16' else 1e-5)
+
+
+def test_nan_inf_and_ties_everywhere(cp):
+    a = rnd((300, 400), 'float32')
+    a[::7, ::11] = np.nan
+    a[5] = 0.25
+    a[:, 17] = -np.inf
+    a[100:120, 30:50] = 0.75
+    d = cp.asarray(a)
+    for ax in (0, 1, None):
+        np.testing.assert_array_equal(d.max(axis=ax).get(), np.max(a, axis=ax))
+        np.testing.assert_array_equal(d.min(axis=ax).get(), np.min(a, axis=ax))
+        np.testing.assert_array_equal(d.argmax(axis=ax).get(), np.argmax(a, axis=ax))
+        np.testing.assert_array_equal(d.argmin(axis=ax).get(), np.argmin(a, axis=ax))
+    h = a.astype(np.float16)
+    np.testing.assert_array_equal(cp.asarray(h).argmax(axis=0).get(), np.argmax(h, axis=0))
+    assert np.isnan(cp.asarray(np.ones(3, np.float32)).var(ddof=3).get())
+
+
+def test_zero_size_and_scalar_arrays(cp):
+    e = cp.empty((0, 3), 'float32')
+    np.testing.assert_array_equal(e.sum(axis=0).get(), np.zeros(3, np.float32))
+    assert e.sum().get() == 0 and e.prod().get() == 1
+    with pytest.raises(ValueError):
+        e.max()
+    assert e.max(axis=1).shape == (0,)
+    s = cp.asarray(np.float32(3.5))
+    assert s.sum().get() == np.float32(3.5) and s.argmax().get() == 0 and s.var().get() == 0
+    assert np.isnan(e.mean().get())
+
+
+# ---------------------------------------------------------------------------------------------
+# 6. scan
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dt', ref_cases.ALL_DTYPES)
+@pytest.mark.parametrize('n', [1, 2, 31, 4095, 4096, 4097, 8193, 100003, (1 << 20) + 5])
+def test_cumsum_sizes(cp, dt, n):
+    a = rnd((n,), dt)
+    got, want = cp.cumsum(cp.asarray(a)).get(), oracle.cumsum(a)
+    assert got.dtype == want.dtype and got.shape == want.shape
+    if want.dtype.kind in 'iu':
+        np.testing.assert_array_equal(got, want)
+    else:
+        run_mag = np.cumsum(np.abs(a.astype(np.float64)))
+        eps = {2: 2e-3, 4: 1e-5, 8: 1e-13}[want.dtype.itemsize]
+        assert (np.abs(got.astype(np.float64) - np.cumsum(a.astype(np.float64))) <= eps * np.maximum(run_mag, 1)).all()
+
+
+def test_scan_variants(cp):
+    a = rnd((50, 60, 7), 'int32')
+    d = cp.asarray(a)
+    np.testing.assert_array_equal(d.cumsum().get(), a.cumsum())
+    for ax in (0, 1, 2, -1):
+        np.testing.assert_array_equal(d.cumsum(axis=ax).get(), a.cumsum(axis=ax))
+    np.testing.assert_array_equal(d.T.cumsum().get(), a.T.cumsum())
+    np.testing.assert_array_equal(cp.cumsum(d, dtype=np.int32).get(), a.cumsum(dtype=np.int32))
+    np.testing.assert_array_equal(cp.cumsum(d, dtype=np.float64).get(), a.cumsum(dtype=np.float64))
+    out = cp.empty((a.size,), np.int64)
+    assert cp.cumsum(d, out=out) is out
+    np.testing.assert_array_equal(out.get(), a.cumsum())
+    x = cp.asarray(np.ones(10000, np.int64))
+    cp.cumsum(x, out=x)                                                     # in place (test_scan.py:50-53)
+    np.testing.assert_array_equal(x.get(), np.arange(1, 10001))
+    p = rnd((40,), 'int64') % 3 + 1
+    np.testing.assert_array_equal(cp.cumprod(cp.asarray(p)).get(), np.cumprod(p))
+    f = (np.abs(rnd((5000,), 'float64')) * 0.01 + 0.995)
+    np.testing.assert_allclose(cp.cumprod(cp.asarray(f)).get(), np.cumprod(f), rtol=1e-11)
+    mis = cp.asarray(np.arange(1001, dtype=np.int64))[1:]                    # 8-byte (not 16-byte) aligned view
+    np.testing.assert_array_equal(mis.cumsum().get(), np.arange(1, 1001).cumsum())
+    np.testing.assert_array_equal(cp.add.accumulate(cp.asarray(p)).get(), np.add.accumulate(p))
+    np.testing.assert_array_equal(cp.add.reduce(d, axis=1).get(), np.add.reduce(a, axis=1))
