@@ -515,6 +515,15 @@ class ndarray:
     def __imul__(self, o): return self._ibinop('multiply', o)
     def __itruediv__(self, o): return self._ibinop('true_divide', o)
 
+    def __lt__(self, o): return self._binop('less', o)
+    def __le__(self, o): return self._binop('less_equal', o)
+    def __gt__(self, o): return self._binop('greater', o)
+    def __ge__(self, o): return self._binop('greater_equal', o)
+    def __eq__(self, o): return self._binop('equal', o)
+    def __ne__(self, o): return self._binop('not_equal', o)
+    __hash__ = None
+    def __pow__(self, o): return self._binop('power', o)
+
     def __neg__(self):
         from cupy_b200._core import _routines_math as m
         return m.negative(self)
@@ -627,18 +636,23 @@ def asarray(a, dtype=None, order=None):
     if hasattr(a, '__cuda_array_interface__'):
         return from_cuda_array_interface(a)
     h = numpy.asarray(a, dtype=dtype)
-    forder = 'F' if (order in ('F', 'f') or (order in (None, 'K', 'A') and h.ndim > 1
-                                             and h.flags.f_contiguous and not h.flags.c_contiguous)) else 'C'
+    # order 'K' (default): keep the memory order of the host array -- upload the bytes of the
+    # axis permutation that is C-contiguous and view them with the permuted strides
     if order in ('C', 'c'):
-        forder = 'C'
-    hc = numpy.asarray(h, order=forder)
-    out = ndarray(hc.shape, hc.dtype, order=forder)
-    if out.size and not _dryrun.enabled:
-        flat = hc.reshape(-1, order=forder).view(numpy.uint8) if hc.dtype != numpy.bool_ else \
-            hc.reshape(-1, order=forder).view(numpy.uint8)
-        src = torch.from_numpy(flat)
-        out._bytes_view().copy_(src, non_blocking=src.is_pinned())
-    return out
+        perm = tuple(range(h.ndim))
+    elif order in ('F', 'f'):
+        perm = tuple(reversed(range(h.ndim)))
+    else:
+        perm = tuple(sorted(range(h.ndim), key=lambda i: (-abs(h.strides[i]), i)))
+    hp = numpy.ascontiguousarray(h.transpose(perm))
+    dev = ndarray(hp.shape, hp.dtype)
+    if dev.size and not _dryrun.enabled:
+        src = torch.from_numpy(hp.reshape(-1).view(numpy.uint8))
+        dev._bytes_view().copy_(src, non_blocking=src.is_pinned())
+    inv = [0] * h.ndim
+    for k, ax in enumerate(perm):
+        inv[ax] = k
+    return dev.transpose(inv) if h.ndim > 1 else dev
 
 
 def array(a, dtype=None, copy=True, order='K'):

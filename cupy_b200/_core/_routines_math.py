@@ -210,9 +210,18 @@ def _scan_flat(src, dst, op):
     st = current_stream_ptr()
     in_id, out_id = _scalar.dtype_id(src.dtype), _scalar.dtype_id(dst.dtype)
     if not _lib.lib.b200_scan_supported(op, in_id, out_id):
-        # stage through the result dtype (one cast pass), as the reference always does
-        tmp = src.astype(dst.dtype)
-        return _scan_flat(tmp, dst, op)
+        # No prebuilt (in, out) pair: scan in the widest accumulator of the result's kind
+        # (modular arithmetic commutes with the final truncation) and cast once at the end.
+        kind = dst.dtype.kind
+        wide = numpy.dtype({'i': 'int64', 'b': 'int64', 'u': 'uint64'}.get(kind, 'float64' if dst.dtype.itemsize == 8 else 'float32'))
+        if _lib.lib.b200_scan_supported(op, in_id, _scalar.dtype_id(wide)):
+            tmp = ndarray(dst.shape, wide)
+            _scan_flat(src, tmp, op)
+        else:
+            tmp = ndarray(dst.shape, wide)
+            _scan_flat(src.astype(wide), tmp, op)
+        _kernel.elementwise_copy(tmp, dst)
+        return
     if src.ptr % 16 or dst.ptr % 16:
         tmp_in = src.copy() if src.ptr % 16 else src
         if dst.ptr % 16:

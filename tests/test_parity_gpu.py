@@ -190,7 +190,7 @@ def test_broadcasting_shapes(cp):
     np.testing.assert_array_equal((cp.asarray(a) * cp.asarray(c)).get(), a * c)
     np.testing.assert_array_equal((cp.asarray(b) - cp.asarray(c)).get(), b - c)
     np.testing.assert_array_equal(cp.add.outer(cp.asarray(c), cp.asarray(c)).get(), np.add.outer(c, c))
-    z = rnd((), 'float32')
+    z = np.float32(0.625)
     np.testing.assert_array_equal((cp.asarray(a) + cp.asarray(z)).get(), a + z)
 
 
