@@ -4,8 +4,13 @@
 // (cupy/cuda/cupy_cub.cu:1163-1185, called from cupy/cuda/cub.pyx:276-306) and,
 // because the input dtype is converted on load, the `astype(order='C')` pre-pass
 // of cupy/_core/_routines_math.pyx:726-727.  No `int num_items` limit: n is 64-bit.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.h"
 #include "include/b200/scan.cuh"
+#include "include/b200/scan_tma.cuh"
+#include "tma_host.h"
 
 namespace b200 {
 
@@ -14,7 +19,99 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(const In* x, Out* y,
     scan_body<In, Acc, Out, Op>(x, y, n, ws);
 }
 
+template <class T, class Op, int THREADS, int STAGES, int LAG>
+__global__ void __launch_bounds__(THREADS) scan_tma_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                           const __grid_constant__ CUtensorMap tm_out,
+                                                           const T* x, T* y, int64_t n,
+                                                           typename LookbackSlot<sizeof(T)>::storage_t* slots) {
+    scan_tma_body<T, Op, THREADS, STAGES, LAG>(&tm_in, &tm_out, x, y, n, slots);
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- TMA-pipelined path (same-size 4 / 8 byte types, large n) -----------------------------
+constexpr int64_t kScanTmaMinN = int64_t(1) << 20;
+constexpr int kScanTmaMinThreads = 128;     // smallest tile = 128 rows of 128 bytes
+
+static size_t scan_tma_ws_bytes(int64_t n) {
+    // worst case over element sizes: 8-byte items, 16 per row, 16-byte slots
+    const int64_t rows = (n + 15) / 16;
+    const int64_t tiles = (rows + kScanTmaMinThreads - 1) / kScanTmaMinThreads;
+    return 16 + 2 * size_t(tiles) * 16;     // per-tile aggregates + per-wave inclusive prefixes
+}
+
+template <class T, class Op, int THREADS, int STAGES, int LAG>
+static int launch_tma(const CUtensorMap& tin, const CUtensorMap& tout, const T* x, T* y, int64_t n, void* wsp,
+                      int sm_count, cudaStream_t stream) {
+    typedef typename LookbackSlot<sizeof(T)>::storage_t slot_t;
+    constexpr int ITEMS = 128 / int(sizeof(T));
+    constexpr int smem = ScanTmaSmem<THREADS, STAGES>::kBytes;
+    auto kern = scan_tma_kernel<T, Op, THREADS, STAGES, LAG>;
+    static int occ = 0;      // per instantiation; benign race
+    if (!occ) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int o = 0;
+        B200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, THREADS, smem));
+        occ = o > 0 ? o : 1;
+    }
+    const int64_t rows = (n + ITEMS - 1) / ITEMS;
+    const int64_t tiles = (rows + THREADS - 1) / THREADS;
+    char* base = static_cast<char*>(wsp);
+    B200_CUDA_TRY(cudaMemsetAsync(base, 0, 16 + 2 * size_t(tiles) * sizeof(slot_t), stream));
+    // every block gathers a whole wave with <= 4 slots per thread: G <= 4 * THREADS
+    const unsigned grid = unsigned(std::min<int64_t>(std::min<int64_t>(tiles, int64_t(sm_count) * occ), 4 * THREADS));
+    slot_t* slots = reinterpret_cast<slot_t*>(base + 16);
+    CUtensorMap tin_v = tin, tout_v = tout;
+    void* args[] = {&tin_v, &tout_v, &x, &y, &n, &slots};
+    // cooperative: the look-back spins on tiles of other blocks, so every block must be resident
+    B200_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(THREADS), args,
+                                              smem, stream));
+    return 0;
+}
+
+// returns B200_E_UNSUPPORTED when the call does not qualify (caller uses the register path)
+template <class T>
+static int run_tma(int op, const void* x, void* y, int64_t n, void* wsp, size_t ws_bytes, cudaStream_t stream) {
+    constexpr int ITEMS = 128 / int(sizeof(T));
+    if (n < kScanTmaMinN || n / ITEMS >= (int64_t(1) << 31)) return B200_E_UNSUPPORTED;
+    if (ws_bytes < scan_tma_ws_bytes(n)) return B200_E_UNSUPPORTED;
+    static int cfg = [] { const char* e = getenv("B200_SCAN_CFG"); return e ? atoi(e) : 0; }();
+    if (cfg < 0) return B200_E_UNSUPPORTED;
+    DeviceInfo di;
+    int st = device_info(&di);
+    if (st) return st;
+    const int threads = (cfg / 100) ? (cfg / 100) * 128 : 256;
+    CUtensorMap tin, tout;
+    const uint64_t dims[2] = {uint64_t(ITEMS), uint64_t(n / ITEMS)};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {uint32_t(ITEMS), uint32_t(threads)};
+    st = make_tensor_map(&tin, sizeof(T), x, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (st) return st;
+    st = make_tensor_map(&tout, sizeof(T), y, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (st) return st;
+    const T* xi = static_cast<const T*>(x);
+    T* yo = static_cast<T*>(y);
+#define B200_TMA_CASE(CODE, TH, ST, LG)                                                                     \
+    if (cfg == CODE) {                                                                                      \
+        if (op == B200_OP_CUMSUM) return launch_tma<T, ScanSum, TH, ST, LG>(tin, tout, xi, yo, n, wsp, di.sm_count, stream); \
+        return launch_tma<T, ScanProd, TH, ST, LG>(tin, tout, xi, yo, n, wsp, di.sm_count, stream);         \
+    }
+    B200_TMA_CASE(0, 256, 6, 3)
+    B200_TMA_CASE(162, 128, 6, 2)
+    B200_TMA_CASE(163, 128, 6, 3)
+    B200_TMA_CASE(252, 256, 5, 2)
+    B200_TMA_CASE(262, 256, 6, 2)
+    B200_TMA_CASE(263, 256, 6, 3)
+#undef B200_TMA_CASE
+    return B200_E_UNSUPPORTED;
+}
+
+template <class In, class Acc, class Out> struct tma_eligible { static constexpr bool value = false; };
+template <> struct tma_eligible<long long, long long, long long> { static constexpr bool value = true; };
+template <> struct tma_eligible<unsigned long long, unsigned long long, unsigned long long> { static constexpr bool value = true; };
+template <> struct tma_eligible<double, double, double> { static constexpr bool value = true; };
+template <> struct tma_eligible<float, float, float> { static constexpr bool value = true; };
+template <> struct tma_eligible<int32_t, int32_t, int32_t> { static constexpr bool value = true; };
 
 static inline int64_t scan_tiles(int64_t n) { return (n + kScanTile - 1) / kScanTile; }
 
@@ -28,6 +125,10 @@ template <class In, class Acc, class Out>
 static int run(int op, const void* x, void* y, int64_t n, void* wsp, size_t ws_bytes, cudaStream_t stream) {
     if (reinterpret_cast<uintptr_t>(x) % 16 || reinterpret_cast<uintptr_t>(y) % 16)
         return fail(B200_E_UNSUPPORTED, "scan needs 16-byte aligned x and y (the host stages misaligned views)");
+    if constexpr (tma_eligible<In, Acc, Out>::value) {
+        const int st = run_tma<In>(op, x, y, n, wsp, ws_bytes, stream);
+        if (st != B200_E_UNSUPPORTED) return st;
+    }
     const size_t tiles = size_t(scan_tiles(n));
     const size_t need = scan_ws_bytes(n, sizeof(Acc));
     if (ws_bytes < need) return fail(B200_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, need);
@@ -87,7 +188,7 @@ extern "C" __attribute__((visibility("default"))) int b200_scan_supported(int op
 extern "C" __attribute__((visibility("default"))) int b200_scan_workspace_bytes(int64_t n, int out_dtype, size_t* bytes) {
     if (!bytes || n < 0) return fail(B200_E_INVALID, "bad argument");
     (void)out_dtype;
-    *bytes = scan_ws_bytes(n, 8);   // widest accumulator
+    *bytes = std::max(scan_ws_bytes(n, 8), scan_tma_ws_bytes(n));   // widest accumulator, either path
     return 0;
 }
 

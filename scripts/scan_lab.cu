@@ -1,0 +1,68 @@
+// Lab harness for the TMA scan (not product code): times scan_tma_body variants on int64.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I cupy_b200/csrc -I include \
+//        -o /tmp/scan_lab scripts/scan_lab.cu cupy_b200/csrc/build/launcher.o -lcuda
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "include/b200/scan_tma.cuh"
+#include "tma_host.h"
+using namespace b200;
+
+template <class T, int THREADS, int STAGES, int LAG, int DBG>
+__global__ void __launch_bounds__(THREADS) k(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout,
+        const T* x, T* y, int64_t n, typename LookbackSlot<sizeof(T)>::storage_t* slots) {
+    scan_tma_body<T, ScanSum, THREADS, STAGES, LAG, DBG>(&tin, &tout, x, y, n, slots);
+}
+
+template <int THREADS, int STAGES, int LAG, int DBG>
+void run(const long long* x, long long* y, int64_t n, char* ws, int maxocc) {
+    typedef long long T;
+    CUtensorMap tin, tout;
+    const uint64_t dims[2] = {16, uint64_t(n / 16)};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {16, THREADS};
+    if (make_tensor_map(&tin, 8, x, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) { printf("tmap fail\n"); return; }
+    make_tensor_map(&tout, 8, y, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    constexpr int smem = ScanTmaSmem<THREADS, STAGES>::kBytes;
+    auto kern = k<T, THREADS, STAGES, LAG, DBG>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem);
+    if (maxocc > 0 && occ > maxocc) occ = maxocc;
+    const int64_t tiles = (n / 16 + THREADS - 1) / THREADS;
+    const unsigned grid = unsigned(std::min<int64_t>(std::min<int64_t>(tiles, 148LL * occ), 4 * THREADS));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e9;
+    for (int r = 0; r < 6; ++r) {
+        cudaMemsetAsync(ws, 0, 16 + 2 * tiles * 16);
+        cudaEventRecord(e0);
+        LookbackSlot<8>::storage_t* slots = (LookbackSlot<8>::storage_t*)(ws + 16);
+        void* args[] = {&tin, &tout, &x, &y, &n, &slots};
+        cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(THREADS), args, smem, 0);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    printf("threads %3d stages %d lag %d dbg %d occ %d grid %5u: %.3f ms  %.0f GB/s %s\n", THREADS, STAGES, LAG, DBG, occ, grid, best,
+           16.0 * n / best / 1e6, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    fflush(stdout);
+}
+
+int main(int argc, char** argv) {
+    const int64_t n = 1LL << 28;
+    long long *x, *y; char* ws;
+    cudaMalloc(&x, n * 8); cudaMalloc(&y, n * 8); cudaMalloc(&ws, 64 << 20);
+    cudaMemset(x, 1, n * 8);
+    for (int mo : {0}) {
+        run<256, 3, 1, 0>(x, y, n, ws, mo); run<256, 4, 1, 0>(x, y, n, ws, mo); run<256, 4, 2, 0>(x, y, n, ws, mo);
+        run<256, 5, 2, 0>(x, y, n, ws, mo); run<256, 5, 3, 0>(x, y, n, ws, mo); run<256, 6, 2, 0>(x, y, n, ws, mo);
+        run<256, 6, 3, 0>(x, y, n, ws, mo); run<256, 6, 4, 0>(x, y, n, ws, mo); run<256, 6, 3, 1>(x, y, n, ws, mo);
+        run<128, 4, 1, 0>(x, y, n, ws, mo); run<128, 4, 2, 0>(x, y, n, ws, mo); run<128, 6, 2, 0>(x, y, n, ws, mo);
+        run<128, 6, 3, 0>(x, y, n, ws, mo); run<128, 6, 4, 0>(x, y, n, ws, mo); run<128, 8, 4, 0>(x, y, n, ws, mo);
+        run<128, 12, 6, 0>(x, y, n, ws, mo); run<128, 12, 8, 0>(x, y, n, ws, mo); run<128, 12, 8, 1>(x, y, n, ws, mo);
+    }
+    return 0;
+}
