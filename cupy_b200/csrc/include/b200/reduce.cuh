@@ -62,6 +62,55 @@ B200_DEVICE typename Op::acc_t merge_lanes(const Op& op, typename Op::acc_t (&ac
 }
 
 // ---------------------------------------------------------------------------
+// ThreadAcc: what a thread keeps while it streams over its share of the reduced
+// axis.  The generic form holds U*V independent lane states of Op::acc_t and
+// folds one element into each per batch.  A functor can replace it with a
+// cheaper representation (fast_lanes<Op>: e.g. arg-reductions keep the batch
+// start index instead of a per-element index and treat NaN out of line) as long
+// as it offers the same four members.
+//   fold(v, j0, us, ks)  one full batch; element (u, k) has reduce-axis index j0 + u*us + k*ks
+//   fold_one(x, j)       one stray element (tails)
+//   result()             everything merged (FULL / ROWS)
+//   result_lane(k)       merged over u only: lane k is its own output column (COLS)
+// ---------------------------------------------------------------------------
+template <class Op> struct fast_lanes { static constexpr bool value = false; };
+
+template <class Op, int U, int V, bool FAST = fast_lanes<Op>::value>
+struct ThreadAcc {
+    typedef typename Op::acc_t acc_t;
+    typedef typename Op::index_t index_t;
+    const Op& op;
+    acc_t acc[U][V];
+    int count;
+    B200_DEVICE explicit ThreadAcc(const Op& op_) : op(op_), count(0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[u][k] = op.identity();
+    }
+    B200_DEVICE void fold(const Pack<typename Op::in_t, V> (&v)[U], index_t j0, index_t us, index_t ks) {
+        const typename Op::ctx_t ctx = op.step(++count);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < V; ++k) op.accumulate(acc[u][k], ctx, v[u][k], j0 + u * us + k * ks);
+    }
+    B200_DEVICE void fold_one(const typename Op::in_t& x, index_t j) {
+        acc[0][0] = op.combine(acc[0][0], op.single(x, j));
+    }
+    B200_DEVICE void fold_one_lane(int k, const typename Op::in_t& x, index_t j) {
+        acc[0][k] = op.combine(acc[0][k], op.single(x, j));
+    }
+    B200_DEVICE acc_t result() { return merge_lanes<Op, U, V>(op, acc); }
+    B200_DEVICE acc_t result_lane(int k) {
+        acc_t a = acc[0][k];
+#pragma unroll
+        for (int u = 1; u < U; ++u) a = op.combine(a, acc[u][k]);
+        return a;
+    }
+};
+
+// ---------------------------------------------------------------------------
 // FULL: x[n] -> y[0].  Persistent grid; each block folds its tiles into
 // U*V lane states per thread, combines through shuffles + shared memory,
 // publishes one partial, and the LAST block to arrive (atomic ticket) folds the
@@ -80,32 +129,20 @@ __device__ __forceinline__ void reduce_full_body(
     acc_t* smem = reinterpret_cast<acc_t*>(smem_raw);
     __shared__ bool is_last;
 
-    acc_t acc[UNROLL][VEC];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[u][k] = op.identity();
-
-    int count = 0;
+    ThreadAcc<Op, UNROLL, VEC> ta(op);
     for (int64_t base = int64_t(blockIdx.x) * kTile; base < n; base += int64_t(gridDim.x) * kTile) {
         if (base + kTile <= n) {
             Pack<typename Op::in_t, VEC> v[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u)
                 load_pack(v[u], x + base + (int64_t(u) * THREADS + threadIdx.x) * VEC);
-            const typename Op::ctx_t ctx = op.step(++count);
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-                for (int k = 0; k < VEC; ++k)
-                    op.accumulate(acc[u][k], ctx, v[u][k],
-                                  static_cast<index_t>(base + (int64_t(u) * THREADS + threadIdx.x) * VEC + k));
+            ta.fold(v, static_cast<index_t>(base + int64_t(threadIdx.x) * VEC), static_cast<index_t>(THREADS * VEC),
+                    static_cast<index_t>(1));
         } else {
-            for (int64_t i = base + threadIdx.x; i < n; i += THREADS)
-                acc[0][0] = op.combine(acc[0][0], op.single(x[i], static_cast<index_t>(i)));
+            for (int64_t i = base + threadIdx.x; i < n; i += THREADS) ta.fold_one(x[i], static_cast<index_t>(i));
         }
     }
-    acc_t r = merge_lanes<Op, UNROLL, VEC>(op, acc);
+    acc_t r = ta.result();
     r = block_combine(op, r, smem);
 
     if (gridDim.x == 1) {
@@ -156,30 +193,19 @@ __device__ __forceinline__ void reduce_rows_body(
         const int64_t row = row0 + gi;
         const bool live = row < rows;
         const typename Op::in_t* __restrict__ xr = x + (live ? row : 0) * n;
-        acc_t acc[UNROLL][VEC];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) acc[u][k] = op.identity();
+        ThreadAcc<Op, UNROLL, VEC> ta(op);
         if (live) {
-            int count = 0;
             int64_t base = 0;
             for (; base + kTile <= n; base += kTile) {
                 Pack<typename Op::in_t, VEC> v[UNROLL];
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) load_pack(v[u], xr + base + (int64_t(u) * GROUP + g) * VEC);
-                const typename Op::ctx_t ctx = op.step(++count);
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k)
-                        op.accumulate(acc[u][k], ctx, v[u][k],
-                                      static_cast<index_t>(base + (int64_t(u) * GROUP + g) * VEC + k));
+                ta.fold(v, static_cast<index_t>(base + int64_t(g) * VEC), static_cast<index_t>(GROUP * VEC),
+                        static_cast<index_t>(1));
             }
-            for (int64_t i = base + g; i < n; i += GROUP)
-                acc[0][0] = op.combine(acc[0][0], op.single(xr[i], static_cast<index_t>(i)));
+            for (int64_t i = base + g; i < n; i += GROUP) ta.fold_one(xr[i], static_cast<index_t>(i));
         }
-        acc_t r = merge_lanes<Op, UNROLL, VEC>(op, acc);
+        acc_t r = ta.result();
         if (GROUP == THREADS) {
             r = block_combine(op, r, smem);
             if (threadIdx.x == 0) y[row] = op.post(r, n);
@@ -222,41 +248,24 @@ __device__ __forceinline__ void reduce_cols_body(
     const int64_t r_end = (r_begin + rows_per_split < n) ? r_begin + rows_per_split : n;
     const typename Op::in_t* __restrict__ xb = x + b * n * cols + c0;
 
-    acc_t acc[RU][VEC];
-#pragma unroll
-    for (int u = 0; u < RU; ++u)
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[u][k] = op.identity();
-
+    ThreadAcc<Op, RU, VEC> ta(op);
     if (col_ok) {
-        int count = 0;
         int64_t r = r_begin + warp;
         for (; r + int64_t(RU - 1) * kWarps < r_end; r += int64_t(RU) * kWarps) {
             Pack<typename Op::in_t, VEC> v[RU];
 #pragma unroll
             for (int u = 0; u < RU; ++u) load_pack(v[u], xb + (r + int64_t(u) * kWarps) * cols);
-            const typename Op::ctx_t ctx = op.step(++count);
-#pragma unroll
-            for (int u = 0; u < RU; ++u)
-#pragma unroll
-                for (int k = 0; k < VEC; ++k)
-                    op.accumulate(acc[u][k], ctx, v[u][k], static_cast<index_t>(r + int64_t(u) * kWarps));
+            ta.fold(v, static_cast<index_t>(r), static_cast<index_t>(kWarps), static_cast<index_t>(0));
         }
         for (; r < r_end; r += kWarps) {
             Pack<typename Op::in_t, VEC> v;
             load_pack(v, xb + r * cols);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k)
-                acc[0][k] = op.combine(acc[0][k], op.single(v[k], static_cast<index_t>(r)));
+            for (int k = 0; k < VEC; ++k) ta.fold_one_lane(k, v[k], static_cast<index_t>(r));
         }
     }
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-        acc_t a = acc[0][k];
-#pragma unroll
-        for (int u = 1; u < RU; ++u) a = op.combine(a, acc[u][k]);
-        smem[warp][lane * VEC + k] = a;
-    }
+    for (int k = 0; k < VEC; ++k) smem[warp][lane * VEC + k] = ta.result_lane(k);
     __syncthreads();
 
     const int64_t tile_c0 = int64_t(blockIdx.x) * kTileCols;

@@ -10,7 +10,10 @@
 //   var             cupy/_core/_routines_statistics.pyx:556-643 (the reference runs
 //                   two passes; here one pass: per-lane Welford + Chan merge)
 #pragma once
+#include <limits>
+
 #include "base.cuh"
+#include "reduce.cuh"
 
 namespace b200 {
 
@@ -107,6 +110,185 @@ struct ExtremumOp {
         if (kArg) return static_cast<out_t>(a.index);
         return static_cast<out_t>(static_cast<In>(a.value));
     }
+};
+
+// ---------------------------------------------------------------------------
+// min / max without an index: one NaN-propagating min/max instruction per element
+// (FMNMX.NAN / HMNMX2.NAN / IMNMX).  +-inf (floats) and the extreme integer are
+// exact identities, so no validity flag is needed.
+// ---------------------------------------------------------------------------
+template <class T> struct ext_type { typedef T type; };            // register type of a running extremum
+template <> struct ext_type<float16> { typedef __half type; };
+
+template <bool kMax> B200_DEVICE float nan_ext(float a, float b) {
+    float r;
+    if (kMax) asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    else asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+template <bool kMax> B200_DEVICE __half nan_ext(__half a, __half b) { return kMax ? __hmax_nan(a, b) : __hmin_nan(a, b); }
+template <bool kMax> B200_DEVICE double nan_ext(double a, double b) {
+    if (a != a) return a;
+    if (b != b) return b;
+    return kMax ? (a > b ? a : b) : (a < b ? a : b);
+}
+template <bool kMax> B200_DEVICE bool nan_ext(bool a, bool b) { return kMax ? (a || b) : (a && b); }
+template <bool kMax, class T> B200_DEVICE T nan_ext(T a, T b) { return kMax ? (a > b ? a : b) : (a < b ? a : b); }
+
+template <class T, bool kMax> struct ext_identity {
+    B200_DEVICE static T get() { return kMax ? std::numeric_limits<T>::lowest() : std::numeric_limits<T>::max(); }
+};
+template <bool kMax> struct ext_identity<float, kMax> {
+    B200_DEVICE static float get() { return kMax ? -__int_as_float(0x7f800000) : __int_as_float(0x7f800000); }
+};
+template <bool kMax> struct ext_identity<double, kMax> {
+    B200_DEVICE static double get() { return kMax ? -__longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0x7ff0000000000000LL); }
+};
+template <bool kMax> struct ext_identity<__half, kMax> {
+    B200_DEVICE static __half get() { return __ushort_as_half(kMax ? (unsigned short)0xfc00 : (unsigned short)0x7c00); }
+};
+template <bool kMax> struct ext_identity<bool, kMax> {
+    B200_DEVICE static bool get() { return !kMax; }
+};
+
+template <class T> B200_DEVICE typename ext_type<T>::type to_ext(const T& v) { return v; }
+template <> B200_DEVICE __half to_ext<float16>(const float16& v) { return v.raw(); }
+template <class T> B200_DEVICE T from_ext(const typename ext_type<T>::type& v) { return v; }
+template <> B200_DEVICE float16 from_ext<float16>(const __half& v) { return float16(v); }
+
+template <class In, bool kMax>
+struct MinMaxOp {
+    typedef In in_t; typedef In out_t; typedef long long index_t; typedef NoCtx ctx_t;
+    typedef typename ext_type<In>::type acc_t;
+    static constexpr bool kWideIndex = false;
+    B200_DEVICE acc_t identity() const { return ext_identity<acc_t, kMax>::get(); }
+    B200_DEVICE ctx_t step(int) const { return ctx_t(); }
+    B200_DEVICE void accumulate(acc_t& a, const ctx_t&, const in_t& v, index_t) const { a = nan_ext<kMax>(a, to_ext(v)); }
+    B200_DEVICE acc_t single(const in_t& v, index_t) const { return to_ext(v); }
+    B200_DEVICE acc_t combine(const acc_t& a, const acc_t& b) const { return nan_ext<kMax>(a, b); }
+    B200_DEVICE out_t post(const acc_t& a, long long) const { return from_ext<In>(a); }
+};
+
+// ---------------------------------------------------------------------------
+// argmin / argmax.  Across threads a (value, index) pair travels (ExtremumOp's
+// combine); inside a thread the streaming state is cheaper (ArgLanes below).
+// ---------------------------------------------------------------------------
+template <class In, class Index, bool kMax>
+struct ArgOp : ExtremumOp<In, long long, Index, kMax, true> {};
+
+template <class T> B200_DEVICE bool ext_is_nan(const T&) { return false; }
+template <> B200_DEVICE bool ext_is_nan<float>(const float& v) { return v != v; }
+template <> B200_DEVICE bool ext_is_nan<double>(const double& v) { return v != v; }
+template <> B200_DEVICE bool ext_is_nan<__half>(const __half& v) { return __hisnan(v); }
+
+// strict "v replaces c"; false when either is NaN
+template <bool kMax, class T> B200_DEVICE bool ext_better(const T& v, const T& c) { return kMax ? (v > c) : (v < c); }
+template <bool kMax> B200_DEVICE bool ext_better(const __half& v, const __half& c) { return kMax ? __hgt(v, c) : __hlt(v, c); }
+
+template <class T> B200_DEVICE typename cmp_type<T>::type ext_to_cmp(const typename ext_type<T>::type& v) { return v; }
+template <> B200_DEVICE float ext_to_cmp<float16>(const __half& v) { return __half2float(v); }
+template <> B200_DEVICE int ext_to_cmp<bool>(const bool& v) { return v ? 1 : 0; }
+
+// Streaming state of an arg-reduction inside a thread: V lanes (one per vector element;
+// in the COLS layout each lane is its own output column), each a running value and the index
+// that set it.  The U elements a lane receives per batch are folded in index order with a
+// strict comparison, so the first occurrence wins and the per-element cost is
+// compare + 2 selects.  The +-inf / extreme-integer start value never wins a comparison
+// against itself: a lane that was never updated reports its first index.  NaN never wins a
+// strict comparison either, so it is detected per batch with a NaN-propagating max
+// (FMNMX3.NAN) and located out of line -- first NaN of each lane.
+template <class In, class Index, bool kMax, int U, int V>
+struct ArgLanes {
+    typedef ArgOp<In, Index, kMax> Op;
+    typedef typename Op::acc_t acc_t;
+    typedef typename ext_type<In>::type E;
+    static constexpr bool kFloat = is_floating<In>::value;
+    const Op& op;
+    E val[V];
+    Index jst[V];        // index (without the lane offset k*ks) of the element that set val; -1 = never updated
+    Index nan_j[V];      // first NaN of the lane (full index); -1 = none
+    Index j_first, ks_;  // first index this thread saw (lane 0, without k*ks); -1 = saw nothing
+
+    B200_DEVICE explicit ArgLanes(const Op& op_) : op(op_), j_first(-1), ks_(0) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { val[k] = ext_identity<E, kMax>::get(); jst[k] = -1; nan_j[k] = -1; }
+    }
+    B200_DEVICE void fold(const Pack<In, V> (&v)[U], Index j0, Index us, Index ks) {
+        ks_ = ks;
+        j_first = j_first < 0 ? j0 : j_first;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const Index ju = j0 + u * us;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const E e = to_ext(v[u][k]);
+                const bool p = ext_better<kMax>(e, val[k]);
+                val[k] = p ? e : val[k];
+                jst[k] = p ? ju : jst[k];
+            }
+        }
+        if (kFloat) {
+            // one NaN test per batch; locating it is rare and kept off the streaming path
+            E m = to_ext(v[0][0]);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < V; ++k)
+                    if (u | k) m = nan_ext<true>(m, to_ext(v[u][k]));
+            if (__builtin_expect(ext_is_nan(m), 0)) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    if (nan_j[k] < 0) {
+#pragma unroll
+                        for (int u = U - 1; u >= 0; --u)
+                            if (ext_is_nan(to_ext(v[u][k]))) nan_j[k] = j0 + u * us + k * ks;
+                    }
+                }
+            }
+        }
+    }
+    // stray elements come after every batch of the lane (larger indices)
+    B200_DEVICE void fold_one_lane(int k, const In& x, Index j) {
+        const E e = to_ext(x);
+        if (k == 0) j_first = j_first < 0 ? j : j_first;
+        const bool p = ext_better<kMax>(e, val[k]);
+        val[k] = p ? e : val[k];
+        jst[k] = p ? (j - k * ks_) : jst[k];
+        if (kFloat && ext_is_nan(e) && nan_j[k] < 0) nan_j[k] = j;
+    }
+    B200_DEVICE void fold_one(const In& x, Index j) { fold_one_lane(0, x, j); }
+    B200_DEVICE acc_t result_lane(int k) {
+        acc_t r = op.identity();
+        // A lane that was never updated holds only start-value elements: its first one counts.
+        // (A lane k > 0 that saw nothing because the thread only took stray elements yields a
+        // start-value candidate too; it can only tie with real start-value elements, and the
+        // lowest index among those is always a real one.)
+        if (j_first >= 0) {
+            r.value = ext_to_cmp<In>(val[k]);
+            r.index = (jst[k] >= 0 ? jst[k] : j_first) + k * ks_;
+        }
+        if (kFloat && nan_j[k] >= 0) {
+            acc_t c;
+            c.value = ext_to_cmp<In>(to_ext(In(__int_as_float(0x7fc00000))));
+            c.index = nan_j[k];
+            r = op.combine(r, c);
+        }
+        return r;
+    }
+    B200_DEVICE acc_t result() {
+        acc_t r = result_lane(0);
+#pragma unroll
+        for (int k = 1; k < V; ++k) r = op.combine(r, result_lane(k));
+        return r;
+    }
+};
+
+template <class In, class Index, bool kMax>
+struct fast_lanes<ArgOp<In, Index, kMax>> { static constexpr bool value = true; };
+
+template <class In, class Index, bool kMax, int U, int V>
+struct ThreadAcc<ArgOp<In, Index, kMax>, U, V, true> : ArgLanes<In, Index, kMax, U, V> {
+    B200_DEVICE explicit ThreadAcc(const ArgOp<In, Index, kMax>& op_) : ArgLanes<In, Index, kMax, U, V>(op_) {}
 };
 
 // Single-pass variance.  Each lane state holds (count, mean, M2) of the

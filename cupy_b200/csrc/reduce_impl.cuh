@@ -237,20 +237,18 @@ static int run_for_type(const b200_reduce_desc_t* d, const void* x, void* y, voi
         }
         case B200_OP_MIN:
             B200_REQUIRE_OUT(T);
-            if (j32) return run_typed<ExtremumOp<T, T, int, false, false>, FV>(ExtremumOp<T, T, int, false, false>(), d, x, y, ws, wsb, s, query, need);
-            return run_typed<ExtremumOp<T, T, long long, false, false>, FV>(ExtremumOp<T, T, long long, false, false>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<MinMaxOp<T, false>, FV>(MinMaxOp<T, false>(), d, x, y, ws, wsb, s, query, need);
         case B200_OP_MAX:
             B200_REQUIRE_OUT(T);
-            if (j32) return run_typed<ExtremumOp<T, T, int, true, false>, FV>(ExtremumOp<T, T, int, true, false>(), d, x, y, ws, wsb, s, query, need);
-            return run_typed<ExtremumOp<T, T, long long, true, false>, FV>(ExtremumOp<T, T, long long, true, false>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<MinMaxOp<T, true>, FV>(MinMaxOp<T, true>(), d, x, y, ws, wsb, s, query, need);
         case B200_OP_ARGMIN:
             B200_REQUIRE_OUT(long long);
-            if (j32) return run_typed<ExtremumOp<T, long long, int, false, true>, FV>(ExtremumOp<T, long long, int, false, true>(), d, x, y, ws, wsb, s, query, need);
-            return run_typed<ExtremumOp<T, long long, long long, false, true>, FV>(ExtremumOp<T, long long, long long, false, true>(), d, x, y, ws, wsb, s, query, need);
+            if (j32) return run_typed<ArgOp<T, int, false>, FV>(ArgOp<T, int, false>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<ArgOp<T, long long, false>, FV>(ArgOp<T, long long, false>(), d, x, y, ws, wsb, s, query, need);
         case B200_OP_ARGMAX:
             B200_REQUIRE_OUT(long long);
-            if (j32) return run_typed<ExtremumOp<T, long long, int, true, true>, FV>(ExtremumOp<T, long long, int, true, true>(), d, x, y, ws, wsb, s, query, need);
-            return run_typed<ExtremumOp<T, long long, long long, true, true>, FV>(ExtremumOp<T, long long, long long, true, true>(), d, x, y, ws, wsb, s, query, need);
+            if (j32) return run_typed<ArgOp<T, int, true>, FV>(ArgOp<T, int, true>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<ArgOp<T, long long, true>, FV>(ArgOp<T, long long, true>(), d, x, y, ws, wsb, s, query, need);
         case B200_OP_MEAN: {
             typedef typename mom_float<T>::type F; typedef typename mom_out<T>::type O;
             B200_REQUIRE_OUT(O);

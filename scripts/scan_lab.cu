@@ -57,12 +57,8 @@ int main(int argc, char** argv) {
     cudaMalloc(&x, n * 8); cudaMalloc(&y, n * 8); cudaMalloc(&ws, 64 << 20);
     cudaMemset(x, 1, n * 8);
     for (int mo : {0}) {
-        run<256, 3, 1, 0>(x, y, n, ws, mo); run<256, 4, 1, 0>(x, y, n, ws, mo); run<256, 4, 2, 0>(x, y, n, ws, mo);
-        run<256, 5, 2, 0>(x, y, n, ws, mo); run<256, 5, 3, 0>(x, y, n, ws, mo); run<256, 6, 2, 0>(x, y, n, ws, mo);
-        run<256, 6, 3, 0>(x, y, n, ws, mo); run<256, 6, 4, 0>(x, y, n, ws, mo); run<256, 6, 3, 1>(x, y, n, ws, mo);
-        run<128, 4, 1, 0>(x, y, n, ws, mo); run<128, 4, 2, 0>(x, y, n, ws, mo); run<128, 6, 2, 0>(x, y, n, ws, mo);
-        run<128, 6, 3, 0>(x, y, n, ws, mo); run<128, 6, 4, 0>(x, y, n, ws, mo); run<128, 8, 4, 0>(x, y, n, ws, mo);
-        run<128, 12, 6, 0>(x, y, n, ws, mo); run<128, 12, 8, 0>(x, y, n, ws, mo); run<128, 12, 8, 1>(x, y, n, ws, mo);
+        run<256, 6, 3, 0>(x, y, n, ws, mo); run<256, 6, 3, 3>(x, y, n, ws, mo); run<256, 6, 3, 1>(x, y, n, ws, mo); run<256, 6, 3, 2>(x, y, n, ws, mo);
+        run<128, 6, 3, 0>(x, y, n, ws, mo); run<128, 6, 3, 3>(x, y, n, ws, mo); run<128, 6, 3, 1>(x, y, n, ws, mo); run<128, 6, 3, 2>(x, y, n, ws, mo);
     }
     return 0;
 }
