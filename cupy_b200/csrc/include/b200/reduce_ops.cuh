@@ -336,4 +336,76 @@ struct MomentsOp {
     }
 };
 
+// ---------------------------------------------------------------------------
+// Streaming state of the single-pass variance inside a thread: V lanes of (mean, M2) that
+// share one element count.  A batch hands every lane U elements; they are folded together:
+//     d_u = x_u - mean        S1 = sum d_u        S2 = sum d_u^2
+//     n' = n + U    delta = S1 / n'    mean' = mean + delta    M2' = M2 + S2 - delta * S1
+// (exactly Chan's merge of the running state with the U-element batch, written around the
+// running mean so nothing large is ever squared).  ~3 flops per element, 2V registers of state
+// whatever U is -- so U can follow the memory system (bytes in flight), not the register file.
+// The very first batch is centred on its own first element.
+// ---------------------------------------------------------------------------
+template <class In, class F, class Out, bool kVar, int U, int V>
+struct MomentLanes {
+    typedef MomentsOp<In, F, Out, kVar> Op;
+    typedef typename Op::acc_t acc_t;
+    typedef typename Op::index_t index_t;
+    const Op& op;
+    F mean[V], m2[V];
+    int batches;             // whole batches folded (n = batches * U per lane)
+    acc_t tail[V];           // stray elements
+    bool any_tail;
+
+    B200_DEVICE explicit MomentLanes(const Op& op_) : op(op_), batches(0), any_tail(false) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { mean[k] = F(0); m2[k] = F(0); tail[k] = op.identity(); }
+    }
+    B200_DEVICE void fold(const Pack<In, V> (&v)[U], index_t, index_t, index_t) {
+        const bool first = batches == 0;
+        ++batches;
+        const F rcp = F(1) / F(batches * U);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const F c = first ? static_cast<F>(v[0][k]) : mean[k];
+            F s1 = F(0), s2 = F(0);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const F d = static_cast<F>(v[u][k]) - c;
+                s1 += d;
+                s2 += d * d;
+            }
+            const F delta = s1 * rcp;
+            mean[k] = c + delta;
+            m2[k] = (m2[k] + s2) - delta * s1;
+        }
+    }
+    B200_DEVICE void fold_one_lane(int k, const In& x, index_t j) {
+        any_tail = true;
+        tail[k] = op.combine(tail[k], op.single(x, j));
+    }
+    B200_DEVICE void fold_one(const In& x, index_t j) { fold_one_lane(0, x, j); }
+    B200_DEVICE acc_t result_lane(int k) {
+        acc_t a;
+        a.n = F(batches * U);
+        a.mean = mean[k];
+        a.m2 = m2[k];
+        return any_tail ? op.combine(a, tail[k]) : a;
+    }
+    B200_DEVICE acc_t result() {
+        acc_t r = result_lane(0);
+#pragma unroll
+        for (int k = 1; k < V; ++k) r = op.combine(r, result_lane(k));
+        return r;
+    }
+};
+
+template <class In, class F, class Out, bool kVar>
+struct fast_lanes<MomentsOp<In, F, Out, kVar>> { static constexpr bool value = true; };
+
+template <class In, class F, class Out, bool kVar, int U, int V>
+struct ThreadAcc<MomentsOp<In, F, Out, kVar>, U, V, true> : MomentLanes<In, F, Out, kVar, U, V> {
+    B200_DEVICE explicit ThreadAcc(const MomentsOp<In, F, Out, kVar>& op_) : MomentLanes<In, F, Out, kVar, U, V>(op_) {}
+};
+
 }  // namespace b200

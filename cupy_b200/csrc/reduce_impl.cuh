@@ -98,10 +98,10 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
     }
     const in_t* x = static_cast<const in_t*>(xv);
     out_t* y = static_cast<out_t*>(yv);
-    constexpr int U = FULLVEC >= 8 ? 2 : 4;    // lane states per thread = U * VEC <= 16
+    constexpr int U = 4;    // 16-byte loads in flight per thread (lane-state cost is the functor's business)
     // COLS keeps 8 warps x 32*VEC accumulators in shared memory: cap it at 32 KiB
     constexpr int CV = (8 * 32 * FULLVEC * int(sizeof(acc_t)) > 32768) ? FULLVEC / 2 : FULLVEC;
-    constexpr int CU = CV >= 8 ? 2 : 4;
+    constexpr int CU = 4;
 
     if (d->layout == B200_RED_FULL) {
         // workspace = [tickets: kTicketBytes][partials]; sized for the widest grid
