@@ -68,19 +68,47 @@ def _fix_cast_expr(src_type, dst_type, expr):
     return expr
 
 
-def _tiler_type(variant, nargs, vec, unroll, threads, idx32):
+_CONTROL_FLOW = re.compile(r'\b(if|else|for|while|do|switch|case|return|goto|continue|break)\b|[{}]')
+
+
+def writes_first(operation, name):
+    """True when every statement of `operation` runs unconditionally and the first mention
+    of output `name` is the left side of a plain assignment at the start of a statement:
+    its previous value can never be observed, so the kernel does not have to load it.
+    (The reference binds outputs as references into memory, cupy/_core/_kernel.pyx:86-97,
+    so an unread output costs it nothing; here operands travel through register packs and
+    a load the compiler cannot prove dead doubles the write traffic.)"""
+    if _CONTROL_FLOW.search(operation):
+        return False
+    m = re.search(r'\b%s\b' % re.escape(name), operation)
+    if m is None:
+        return False
+    before = operation[:m.start()].rstrip()
+    after = operation[m.end():].lstrip()
+    return (before == '' or before.endswith(';')) and after.startswith('=') and not after.startswith('==')
+
+
+def _tiler_type(variant, nargs, vec, unroll, threads, idx32, spec=0):
     if variant == _lib.EW_FLAT:
         return 'b200::FlatTiler<%d, %d, %d, %d>' % (nargs, vec, unroll, threads)
     if variant == _lib.EW_ROWWISE:
         return 'b200::RowTiler<%d, %d, %d, %d, %s>' % (nargs, vec, unroll, threads, 'true' if idx32 else 'false')
+    if variant == _lib.EW_TILED_TMA:
+        return 'b200::TmaTileTiler<%d, %d>' % (nargs, 16 // vec)
+    if variant == _lib.EW_TILED_REG:
+        return 'b200::RegTileTiler<%d, %d, %d, %dull>' % (nargs, 16 // vec, unroll, spec)
     return 'b200::TileTiler<%d>' % nargs
 
 
-def render_elementwise(spec, name, args, params, variant, vec, unroll, threads, idx32, ndim):
+def render_elementwise(spec, name, args, params, variant, vec, unroll, threads, idx32, ndim, access_spec=0,
+                       min_blocks=1):
     from cupy_b200._core._ndarray import ndarray
     nargs = len(args)
     if variant == _lib.EW_TILED:
         vec, unroll, threads = 1, 4, 256
+    tma = variant == _lib.EW_TILED_TMA
+    if tma:
+        unroll, threads = vec, 288    # 8 consumer warps + the TMA producer warp
     lines = [_PROLOGUE]
     for ctype, dt in spec.type_map:
         lines.append('typedef %s %s;' % (get_typename(dt), ctype))
@@ -92,10 +120,11 @@ def render_elementwise(spec, name, args, params, variant, vec, unroll, threads, 
             typedefs.append('typedef %s out%d_type;' % (get_typename(t), k))
     lines.extend(typedefs)
     lines.append(spec.preamble)
-    lines.append('extern "C" __global__ void __launch_bounds__(%d) %s('
-                 'const __grid_constant__ b200::EwParams _p, const __grid_constant__ b200::RawPack _rv) {'
-                 % (threads, name))
-    lines.append('  typedef %s _Tiler;' % _tiler_type(variant, nargs, vec, unroll, threads, idx32))
+    min_blocks = ', %d' % min_blocks if variant == _lib.EW_TILED_REG else ''
+    lines.append('extern "C" __global__ void __launch_bounds__(%d%s) %s('
+                 'const __grid_constant__ b200::EwParams _p, const __grid_constant__ b200::RawPack _rv%s) {'
+                 % (threads, min_blocks, name, ', const __grid_constant__ b200::TileMaps _tm' if tma else ''))
+    lines.append('  typedef %s _Tiler;' % _tiler_type(variant, nargs, vec, unroll, threads, idx32, access_spec))
     lines.append('  constexpr int _V = _Tiler::kV, _U = _Tiler::kU;')
 
     decl, loads, binds, stores = [], [], [], []
@@ -131,9 +160,10 @@ def render_elementwise(spec, name, args, params, variant, vec, unroll, threads, 
                         reg, _fix_cast_expr(spec.out_types[idx], a.dtype, 'out%d' % idx)),
                         '    _t.template store<_FULL>(%d, %s);' % (k, reg)))
             else:
-                # user kernel: outputs are read-modify-write capable; an unread
-                # load is removed by the compiler
-                loads.append('    _t.template load<_FULL>(%d, %s);' % (k, reg))
+                # user kernel: outputs are read-modify-write capable unless the operation
+                # provably writes them first
+                if not (is_out and writes_first(spec.operation, p.name)):
+                    loads.append('    _t.template load<_FULL>(%d, %s);' % (k, reg))
                 if is_out:
                     binds.append('        %s& %s = %s[_u][_k];' % (p.ctype, p.name, reg))
                     stores.append((None, '    _t.template store<_FULL>(%d, %s);' % (k, reg)))
@@ -151,7 +181,7 @@ def render_elementwise(spec, name, args, params, variant, vec, unroll, threads, 
     lines.extend(decl)
     lines.append('  CIndexer<%d> _ind(_p.size, _p.shape);' % (ndim if spec.uses_ind else 1))
     lines.append('  ' + spec.loop_prep + ';')
-    lines.append('  _Tiler _t(_p);')
+    lines.append('  _Tiler _t(_p, _tm);' if tma else '  _Tiler _t(_p);')
     lines.append('  auto _tile = [&](auto _full_tag) {')
     lines.append('    constexpr bool _FULL = decltype(_full_tag)::value;')
     lines.extend(loads)

@@ -323,6 +323,9 @@ tunables = {
     'flat_unroll': 4,
     'row_unroll': 2,
     'blocks_per_sm': 0,       # 0 = library default
+    'tma_stages': 0,          # TILED_TMA ring depth, 0 = library default
+    'reg_unroll': 0,          # TILED_REG blocks per thread, 0 = library default (8 vector loads in flight)
+    'reg_min_blocks': 0,      # TILED_REG __launch_bounds__ min blocks/SM, 0 = from the register estimate
 }
 
 
@@ -332,6 +335,16 @@ def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stre
     threads = tunables['threads'] if block_size is None else int(block_size)
     if variant == _lib.EW_TILED:
         threads, unroll, vec = 256, 4, 1
+    elif variant == _lib.EW_TILED_REG:
+        esz = 16 // plan.vec
+        # 8 vector loads of the staged operand in flight for unary calls (== b200::reg_tile_unroll());
+        # half of that with more operands: occupancy hides the latency better than registers do there
+        # (B200 sweep in profiles/r01_tiled_lab.md)
+        n_arrays = sum(1 for o in ops if o.kind == _lib.KIND_ARRAY)
+        unroll = tunables['reg_unroll'] or ({4: 2, 2: 1, 8: 4}[esz] if n_arrays <= 2 else {4: 1, 2: 1, 8: 2}[esz])
+        threads, vec = 256, plan.vec
+    elif variant == _lib.EW_TILED_TMA:
+        threads, unroll, vec = 288, tunables['tma_stages'], plan.vec   # "unroll" slot = ring depth override (0 = auto)
     elif variant == _lib.EW_FLAT:
         unroll, vec = tunables['flat_unroll'], plan.vec
     else:
@@ -340,16 +353,38 @@ def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stre
         ('raw', a.dtype.char, a.ndim, a._c_contiguous) if (isinstance(a, ndarray) and p.raw)
         else ('arr', a.dtype.char) if isinstance(a, ndarray) else ('scalar', a.descr.char)
         for a, p in zip(args, params))
-    key = (name, variant, vec, unroll, threads, bool(plan.idx32), plan.ndim if spec.uses_ind else -1, arginfo)
+    access, min_blocks = 0, 1
+    if variant == _lib.EW_TILED_REG:
+        # per-operand access, fixed at compile time (RegTileTiler SPEC, 3 bits each): staged /
+        # unit along O / other, plus "broadcast along I"; registers a thread's blocks take
+        last, ax = plan.ndim - 1, plan.tile_axis
+        block_regs = unroll * plan.vec * plan.vec * esz // 4
+        regs_in = regs_out = 0
+        for k, o in enumerate(ops):
+            if o.kind != _lib.KIND_ARRAY:
+                continue
+            bits = 1 if (plan.staged_mask >> k) & 1 else 2 if plan.strides[k][last] == esz else 3
+            regs = block_regs
+            if bits != 1 and plan.strides[k][ax] == 0:
+                bits |= 4
+                regs //= plan.vec
+            access |= bits << (3 * k)
+            if o.is_output:
+                regs_out += regs
+            else:
+                regs_in += regs
+        est = max(regs_in, regs_out) + (64 if esz == 2 else 30)
+        min_blocks = tunables['reg_min_blocks'] or max(1, min(3 if n_arrays <= 2 else 5, 65536 // (256 * est)))
+    key = (name, variant, vec, unroll, threads, bool(plan.idx32), plan.ndim if spec.uses_ind else -1, arginfo, access, min_blocks)
     fn = spec.memo.get(key)
     if fn is None:
         source = _codegen.render_elementwise(
             spec, name, args, params, variant=variant, vec=vec, unroll=unroll, threads=threads,
-            idx32=bool(plan.idx32), ndim=plan.ndim)
+            idx32=bool(plan.idx32), ndim=plan.ndim, access_spec=access, min_blocks=min_blocks)
         spec.last_source = source
         fn = _jit.get_function(source, name, spec.options)
         spec.memo[key] = fn
-    plan.reserved = (unroll & 0xff) | ((tunables['blocks_per_sm'] & 0xffff) << 8)
+    plan.reserved = (plan.reserved & 0xff000000) | (unroll & 0xff) | ((tunables['blocks_per_sm'] & 0xffff) << 8)
     if _dryrun.enabled:
         _dryrun.record('jit_elementwise', name=name, variant=variant, vec=vec, ndim=plan.ndim,
                        idx32=bool(plan.idx32), staged_mask=plan.staged_mask, tile_axis=plan.tile_axis,
@@ -734,7 +769,9 @@ class ufunc:
         st = current_stream_ptr()
 
         # ---- prebuilt kernel?
+        # (register-tiled calls are prebuilt for unary ufuncs only; NVRTC fixes each operand's access otherwise)
         if (self._prebuilt is not None and not has_where and self.nout == 1
+                and not (plan.variant == _lib.EW_TILED_REG and self.nin > 1)
                 and all(a.dtype == t if isinstance(a, ndarray) else True for a, t in zip(in_args, op.in_types))
                 and (self._prebuilt == 0 or out_args[0].dtype == op.out_types[0])):
             in_ids = (ctypes.c_int32 * self.nin)(*[_scalar.dtype_id(t) for t in op.in_types])

@@ -30,7 +30,7 @@ OP_SUM, OP_MIN, OP_MAX, OP_ARGMIN, OP_ARGMAX, OP_CUMSUM, OP_CUMPROD, OP_PROD, \
 OK, E_INVALID, E_UNSUPPORTED, E_WORKSPACE, E_NOLIB, E_COMPILE = 0, -1, -2, -3, -4, -5
 
 KIND_ARRAY, KIND_SCALAR, KIND_RAW = 0, 1, 2
-EW_FLAT, EW_ROWWISE, EW_TILED = 0, 1, 2
+EW_FLAT, EW_ROWWISE, EW_TILED, EW_TILED_TMA, EW_TILED_REG = 0, 1, 2, 3, 4
 RED_FULL, RED_ROWS, RED_COLS = 0, 1, 2
 
 UFUNC_IDS = {name: i for i, name in enumerate((

@@ -37,6 +37,12 @@ inline int dtype_size(int dtype) {
 // Build the by-value kernel parameter block from a plan and its operands.
 int fill_ew_params(const b200_ew_plan_t* plan, int nargs, const b200_operand_t* args, EwParams* out);
 
+// TILED_TMA: tile geometry, ring depth + dynamic shared memory, tensor maps of the staged operands
+void tma_tile_geometry(const b200_ew_plan_t* plan, int* esz, int* tile_i, int* tile_o);
+int tma_blocks_per_sm(const b200_ew_plan_t* plan);
+void tma_ring(const b200_ew_plan_t* plan, int* stages, unsigned* smem_bytes);
+int build_tile_maps(const b200_ew_plan_t* plan, const b200_operand_t* args, TileMaps* out);
+
 // Grid size for a persistent elementwise launch.
 unsigned ew_grid(const b200_ew_plan_t* plan, int threads, int unroll, int sm_count);
 

@@ -89,6 +89,25 @@ extern "C" __attribute__((visibility("default"))) int b200_ufunc_launch(int ufun
         case B200_EW_TILED:
             fn = k->tiled;
             break;
+        case B200_EW_TILED_REG:
+            if (!k->tiled_reg) return fail(B200_E_UNSUPPORTED, "no register-tiled prebuilt kernel for ufunc %d", ufunc);
+            fn = k->tiled_reg;
+            break;
+        case B200_EW_TILED_TMA: {
+            if (!k->tiled_tma) return fail(B200_E_UNSUPPORTED, "no TMA-tiled prebuilt kernel for ufunc %d", ufunc);
+            TileMaps tm;
+            st = build_tile_maps(plan, args, &tm);
+            if (st) return st;
+            int stages;
+            unsigned smem;
+            tma_ring(plan, &stages, &smem);
+            p.tma_stages = stages;
+            B200_CUDA_TRY(cudaFuncSetAttribute(k->tiled_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            const unsigned g = ew_grid(plan, 288, 1, di.sm_count);
+            void* targs[] = {&p, &tm};
+            B200_CUDA_TRY(cudaLaunchKernel(k->tiled_tma, dim3(g), dim3(288), targs, smem, static_cast<cudaStream_t>(stream)));
+            return 0;
+        }
         default:
             return fail(B200_E_INVALID, "bad plan variant %d", plan->variant);
     }

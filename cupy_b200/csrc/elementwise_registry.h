@@ -14,6 +14,8 @@ struct EwKernels {
     const void* row_164;     // ROWWISE, scalar, 64-bit index
     const void* row_v64;     // ROWWISE, vector, 64-bit index
     const void* tiled;
+    const void* tiled_reg;   // TILED_REG (same eligibility as tiled_tma)
+    const void* tiled_tma;   // TILED_TMA (nullptr unless all operand item sizes are equal and 2/4/8 bytes)
     int vec;                 // "full" vector width of this instantiation
     int unroll_flat, unroll_row;
 };

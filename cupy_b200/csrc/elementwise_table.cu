@@ -63,13 +63,44 @@ __device__ __forceinline__ void ew_tile(const Tiler& t, const EwParams& p) {
     t.template store<FULL>(F::nin, o);
 }
 
-template <class Tiler, class F>
-__global__ void __launch_bounds__(kEwThreads) ew_kernel(const __grid_constant__ EwParams p) {
+template <class Tiler, class F, int MIN_BLOCKS = 1>
+__global__ void __launch_bounds__(kEwThreads, MIN_BLOCKS) ew_kernel(const __grid_constant__ EwParams p) {
     Tiler t(p);
     for (; t.valid(); t.next()) {
         if (t.is_full()) ew_tile<true, Tiler, F>(t, p);
         else ew_tile<false, Tiler, F>(t, p);
     }
+}
+
+template <class Tiler, class F>
+__global__ void __launch_bounds__(Tiler::kThreads) ew_tma_kernel(const __grid_constant__ EwParams p,
+                                                                 const __grid_constant__ TileMaps tm) {
+    Tiler t(p, tm);
+    for (; t.valid(); t.next()) {
+        if (t.is_full()) ew_tile<true, Tiler, F>(t, p);
+        else ew_tile<false, Tiler, F>(t, p);
+    }
+}
+
+template <class F, bool OK> struct TmaKernelOf { static const void* get() { return nullptr; } };
+template <class F> struct TmaKernelOf<F, true> {
+    static const void* get() {
+        return reinterpret_cast<const void*>(&ew_tma_kernel<TmaTileTiler<F::nin + 1, int(sizeof(typename F::out_t))>, F>);
+    }
+};
+// TILED_REG is prebuilt for unary ufuncs only (input staged, output unit-stride: SPEC known);
+// calls with more operands go through NVRTC, where the generator fixes each operand's access.
+template <class F, bool OK> struct RegKernelOf { static const void* get() { return nullptr; } };
+template <class F> struct RegKernelOf<F, true> {
+    static const void* get() {
+        constexpr int e = int(sizeof(typename F::out_t));
+        return reinterpret_cast<const void*>(&ew_kernel<RegTileTiler<2, e, reg_tile_unroll(e), (1ull | (2ull << 3))>, F, (e == 2 ? 2 : 3)>);
+    }
+};
+template <class F> constexpr bool tma_eligible() {
+    constexpr int so = int(sizeof(typename F::out_t));
+    return (so == 2 || so == 4 || so == 8) && int(sizeof(typename F::in0_t)) == so &&
+           (F::nin < 2 || int(sizeof(typename F::in1_t)) == so) && (F::nin < 3 || int(sizeof(typename F::in2_t)) == so);
 }
 
 template <class T> constexpr int max_size2(int a) { return int(sizeof(T)) > a ? int(sizeof(T)) : a; }
@@ -88,6 +119,8 @@ static EwKernels make_kernels() {
     k.row_164 = reinterpret_cast<const void*>(&ew_kernel<RowTiler<N, 1, UR, kEwThreads, false>, F>);
     k.row_v64 = reinterpret_cast<const void*>(&ew_kernel<RowTiler<N, V, UR, kEwThreads, false>, F>);
     k.tiled = reinterpret_cast<const void*>(&ew_kernel<TileTiler<N>, F>);
+    k.tiled_tma = TmaKernelOf<F, tma_eligible<F>()>::get();
+    k.tiled_reg = RegKernelOf<F, tma_eligible<F>() && F::nin == 1>::get();
     k.vec = V;
     k.unroll_flat = UF;
     k.unroll_row = UR;

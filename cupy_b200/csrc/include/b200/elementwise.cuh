@@ -19,6 +19,7 @@
 // its per-element CIndexer div/mod (carray.cuh:588-615).
 #pragma once
 #include "base.cuh"
+#include "tma.cuh"
 
 namespace b200 {
 
@@ -36,11 +37,18 @@ struct EwParams {
     int32_t  tile_axis;            // TILED only
     uint32_t staged_mask;          // TILED only
     uint32_t scalar_mask;          // bit k set = operand k is a by-value scalar
+    int32_t  tma_stages;           // TILED_TMA only: depth of the shared-memory tile ring
+    int32_t  tma_pad_;
     int64_t  shape[kMaxNdim];
     int64_t  cstride[kMaxNdim];    // C-order element strides of `shape` (for the linear index `i`)
     FastDiv  fdiv[kMaxNdim];       // fast division by shape[d] (valid when size < 2^31)
     EwArg    arg[kMaxArgs];
 };
+
+// TILED_TMA: one opaque 128-byte CUtensorMap per staged operand (in operand order)
+constexpr int kMaxStaged = 4;
+struct alignas(64) TensorMapBlob { uint64_t v[16]; };
+struct TileMaps { TensorMapBlob m[kMaxStaged]; };
 
 struct true_t { static constexpr bool value = true; };
 struct false_t { static constexpr bool value = false; };
@@ -339,6 +347,382 @@ struct TileTiler {
         for (int u = 0; u < 4; ++u)
             if (in_range<FULL>(u, 0))
                 *reinterpret_cast<T*>(base + (i0 + ty + 8 * u) * s_i + (o0 + tx) * s_o) = r[u][0];
+    }
+};
+
+// ---------------------------------------------------------------------------
+// TILED_TMA: the same transposing call as TILED, on the sm_100a copy engine.
+// Every array operand has the same item size ESZ (2, 4 or 8 bytes).
+//
+//   tile     = kTI x kTO elements (I x O); a staged operand's tile is kTO rows
+//              of 128 bytes (kTI elements along I), fetched by ONE TMA tensor
+//              copy (5-D map: I, O, batch dims) with 128-byte swizzle.
+//   block    = 8 consumer warps + 1 producer warp (288 threads), persistent
+//              over tiles.  The producer warp lives entirely inside the
+//              constructor: it keeps `tma_stages` tiles in flight through a
+//              full/empty mbarrier ring, so the bytes in flight per SM are set
+//              by the ring depth and not by occupancy or register count.
+//   consumer = each lane reads kV 16-byte chunks (rows o..o+kV-1, one chunk of
+//              kCH elements along I) with conflict-free LDS.128 and owns the
+//              kCH x kV register block they form: the transpose itself is
+//              register renaming, r[u][k] = chunk[k][u].  Compute, direct
+//              operands and outputs then run along O with 128-bit accesses.
+// ---------------------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char b200_dyn_smem[];
+
+template <int NARGS, int ESZ>
+struct TmaTileTiler {
+    static constexpr int kCH = 16 / ESZ;                  // elements per 16-byte chunk
+    static constexpr int kV = kCH, kU = kCH;
+    static constexpr int kTI = 128 / ESZ;                 // 8 chunks
+    static constexpr int kLanesI = (kCH == 4) ? 4 : 8;    // lanes along I (chunks); see bank note below
+    static constexpr int kLanesO = 32 / kLanesI;
+    static constexpr int kWarpsI = 8 / kLanesI;
+    static constexpr int kWarpsO = 8 / kWarpsI;
+    static constexpr int kTO = kWarpsO * kLanesO * kV;    // 128 (4 B), 256 (2 B), 64 (8 B)
+    static constexpr int kTileBytes = kTO * 128;
+    static constexpr int kThreads = 288;
+    static constexpr int kMaxStages = 8;
+    // Bank note: a quarter-warp (8 lanes) must hit 8 distinct 16-byte bank groups.
+    // Physical chunk = chunk ^ (row & 7).  With 8 lanes along I the row is shared
+    // and the chunks differ; with 4 lanes along I (kV == 4) the two rows of a
+    // quarter-warp differ by 4, which flips bit 2 of the XOR and separates them.
+
+    const EwParams& p;
+    const TileMaps& tm;
+    int64_t n_i, n_o, i0, o0, lin0;
+    int64_t boff[NARGS];
+    uint32_t tiles_i, tiles_o, tiles, t;
+    uint32_t bars, ring;          // shared-window addresses: barriers, first stage
+    int stage, phase, last_staged;
+    int li, lo, chunk;            // lane's element offsets inside the tile, chunk index
+    bool live;
+
+    B200_DEVICE uint32_t full_bar(int s) const { return bars + 8u * s; }
+    B200_DEVICE uint32_t empty_bar(int s) const { return bars + 8u * (kMaxStages + s); }
+
+    B200_DEVICE TmaTileTiler(const EwParams& p_, const TileMaps& tm_) : p(p_), tm(tm_) {
+        const int ax_i = p.tile_axis, ax_o = p.ndim - 1;
+        n_i = p.shape[ax_i];
+        n_o = p.shape[ax_o];
+        tiles_i = static_cast<uint32_t>((n_i + kTI - 1) / kTI);
+        tiles_o = static_cast<uint32_t>((n_o + kTO - 1) / kTO);
+        tiles = static_cast<uint32_t>((p.size / (n_i * n_o)) * tiles_i * tiles_o);
+        const int nstaged = __popc(p.staged_mask);
+        last_staged = 31 - __clz(p.staged_mask);
+        const int S = p.tma_stages;
+        bars = smem_u32(b200_dyn_smem);
+        ring = (bars + 16u * kMaxStages + 1023u) & ~1023u;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < S; ++s) {
+                mbar_init_a(full_bar(s), 1);
+                mbar_init_a(empty_bar(s), 8);
+            }
+            mbar_fence_init();
+        }
+        __syncthreads();
+        t = blockIdx.x;
+        stage = 0;
+        phase = 0;
+        if (warp == 8) {
+            // ---- producer: runs to completion here, then leaves the loop idle
+            if (lane == 0) {
+                for (int a = 0; a < NARGS; ++a)
+                    if ((p.staged_mask >> a) & 1u) tma_prefetch_desc(&tm.m[__popc(p.staged_mask & ((1u << a) - 1u))]);
+                uint32_t k = 0;
+                for (; t < tiles; t += gridDim.x, ++k) {
+                    if (k >= uint32_t(S)) mbar_wait_a(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx_a(full_bar(stage), uint32_t(nstaged) * kTileBytes);
+                    uint32_t b = t;
+                    int32_t c[5] = {0, 0, 0, 0, 0};
+                    c[0] = int32_t((b % tiles_i) * kTI);
+                    b /= tiles_i;
+                    c[1] = int32_t((b % tiles_o) * kTO);
+                    b /= tiles_o;
+                    int n = 2;
+#pragma unroll 1
+                    for (int d = p.ndim - 2; d >= 0; --d) {
+                        if (d == ax_i) continue;
+                        const uint32_t s = static_cast<uint32_t>(p.shape[d]);
+                        c[n++] = int32_t(b % s);
+                        b /= s;
+                    }
+                    uint32_t dst = ring + uint32_t(stage) * uint32_t(nstaged) * kTileBytes;
+                    for (int a = 0; a < NARGS; ++a) {
+                        if (!((p.staged_mask >> a) & 1u)) continue;
+                        const int slot = __popc(p.staged_mask & ((1u << a) - 1u));
+                        tma_load_5d(dst, &tm.m[slot], c[0], c[1], c[2], c[3], c[4], full_bar(stage));
+                        dst += kTileBytes;
+                    }
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+            live = false;
+            return;
+        }
+        // ---- consumers
+        const int wi = warp % kWarpsI, wo = warp / kWarpsI;
+        chunk = wi * kLanesI + (lane % kLanesI);
+        li = chunk * kCH;
+        lo = (wo * kLanesO + lane / kLanesI) * kV;
+        live = t < tiles;
+        if (live) locate();
+    }
+
+    B200_DEVICE void locate() {
+        const int ax_i = p.tile_axis;
+        uint32_t b = t;
+        i0 = int64_t(b % tiles_i) * kTI;
+        b /= tiles_i;
+        o0 = int64_t(b % tiles_o) * kTO;
+        b /= tiles_o;
+        lin0 = 0;
+#pragma unroll
+        for (int a = 0; a < NARGS; ++a) boff[a] = 0;
+#pragma unroll 1
+        for (int d = p.ndim - 2; d >= 0; --d) {
+            if (d == ax_i) continue;
+            const uint32_t s = static_cast<uint32_t>(p.shape[d]);
+            const uint32_t r = b % s;
+            b /= s;
+            lin0 += int64_t(r) * p.cstride[d];
+#pragma unroll
+            for (int a = 0; a < NARGS; ++a) boff[a] += int64_t(r) * p.arg[a].strides[d];
+        }
+    }
+    B200_DEVICE bool valid() const { return live; }
+    B200_DEVICE void next() {
+        t += gridDim.x;
+        if (++stage == p.tma_stages) { stage = 0; phase ^= 1; }
+        live = t < tiles;
+        if (live) locate();
+    }
+    B200_DEVICE bool is_full() const { return i0 + kTI <= n_i && o0 + kTO <= n_o; }
+    template <bool FULL>
+    B200_DEVICE bool in_range(int u, int k) const { return FULL || ((i0 + li + u) < n_i && (o0 + lo + k) < n_o); }
+    B200_DEVICE int64_t index(int u, int k) const {
+        return lin0 + (i0 + li + u) * p.cstride[p.tile_axis] + (o0 + lo + k);
+    }
+
+    template <bool FULL, class T>
+    B200_DEVICE void load(int a, Pack<T, kV> (&r)[kU]) const {
+        static_assert(sizeof(T) == ESZ, "TILED_TMA: every array operand has the tile's item size");
+        if ((p.staged_mask >> a) & 1u) {
+            const int nstaged = __popc(p.staged_mask);
+            const int slot = __popc(p.staged_mask & ((1u << a) - 1u));
+            mbar_wait_a(full_bar(stage), uint32_t(phase));
+            const uint32_t tb = ring + (uint32_t(stage) * uint32_t(nstaged) + uint32_t(slot)) * kTileBytes;
+            uint4 q[kV];
+#pragma unroll
+            for (int k = 0; k < kV; ++k) q[k] = ld_shared_v4(tb + swz128(uint32_t(lo + k), uint32_t(chunk)));
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+#pragma unroll
+                for (int k = 0; k < kV; ++k) r[u][k] = reinterpret_cast<const T*>(&q[k])[u];
+            if (a == last_staged) {
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) mbar_arrive_a(empty_bar(stage));
+            }
+        } else {
+            const int64_t s_i = p.arg[a].strides[p.tile_axis];
+            const int64_t s_o = p.arg[a].strides[p.ndim - 1];
+            const char* base = p.arg[a].ptr + boff[a] + (i0 + li) * s_i + (o0 + lo) * s_o;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (!FULL && !in_range<false>(u, 0)) continue;
+                const char* q = base + u * s_i;
+                if (s_o == int64_t(sizeof(T))) {
+                    load_pack(r[u], reinterpret_cast<const T*>(q));
+                } else if (s_o == 0) {
+                    const T v = *reinterpret_cast<const T*>(q);
+#pragma unroll
+                    for (int k = 0; k < kV; ++k) r[u][k] = v;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kV; ++k) r[u][k] = *reinterpret_cast<const T*>(q + k * s_o);
+                }
+            }
+        }
+    }
+    template <bool FULL, class T>
+    B200_DEVICE void store(int a, const Pack<T, kV> (&r)[kU]) const {
+        const int64_t s_i = p.arg[a].strides[p.tile_axis];
+        char* base = p.arg[a].ptr + boff[a] + (i0 + li) * s_i + (o0 + lo) * int64_t(sizeof(T));
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+            if (FULL || in_range<false>(u, 0)) store_pack(reinterpret_cast<T*>(base + u * s_i), r[u]);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// TILED_REG: register-block transpose, the default for transposing calls whose
+// array operands share one item size ESZ (2, 4 or 8 bytes) and are 16-byte
+// aligned.  No shared memory, no barriers:
+//
+//   lane     = a CH x CH block of elements (CH = 16 / ESZ).  A staged operand is
+//              read as CH 16-byte vectors along I (rows o .. o+CH-1); direct
+//              operands and outputs are CH vectors along O (rows i .. i+CH-1);
+//              between the two the block is only renamed, r[a][k] = q[k][a].
+//   warp     = 8 lanes along I x 4 lanes along O: every load instruction covers
+//              4 rows of 128 contiguous bytes, every store 8 rows of 64 bytes
+//              (whole 32-byte sectors on both sides).
+//   thread   = UN such blocks (8 vector loads in flight), block = 8 warps; the
+//              8*UN warp units of a tile are laid along O first (long output
+//              rows), the rest along I.  Persistent grid-stride over tiles.
+//
+// Measured on config 4a (scripts/regblock_lab.cu, tma_read_lab.cu): 5.57 TB/s
+// against 4.75 TB/s for the TMA ring (TILED_TMA), whose tensor copies are bound
+// by address translation at ~16 B/clk/SM when every 128-byte box row lies in a
+// different 2 MB page; plain LDG.128 on the same rows reads at 7.0 TB/s.
+// ---------------------------------------------------------------------------
+// blocks per thread: 8 vector loads of the staged operand in flight
+B200_HD constexpr int reg_tile_unroll(int esz) { return esz == 4 ? 2 : esz == 2 ? 1 : 4; }
+B200_HD int reg_tile_units_o(int64_t n_o, int unit_o, int units) {
+    const int64_t need = (n_o + unit_o - 1) / unit_o;
+    int u = 1;
+    while (u < units && u < need) u <<= 1;
+    return u;
+}
+
+// SPEC: three bits per operand fixing its access at compile time (the prebuilt unary
+// table and every JIT kernel know the strides when the kernel is chosen):
+//   bits 0-1: 1 = staged (unit-stride along I), 2 = direct, unit-stride along O,
+//             3 = direct, broadcast or strided along O (scalar accesses);
+//   bit 2   : direct operand with stride 0 along I -> one row serves the whole block.
+template <int NARGS, int ESZ, int UN, uint64_t SPEC>
+struct RegTileTiler {
+    static constexpr int kCH = 16 / ESZ;
+    static constexpr int kV = kCH, kU = kCH * UN;
+    static constexpr int kLanesI = 8, kLanesO = 4;
+    static constexpr int kUnitI = kLanesI * kCH;      // elements along I of one warp unit (128 bytes)
+    static constexpr int kUnitO = kLanesO * kCH;      // elements along O of one warp unit (64 bytes)
+    static constexpr int kUnits = 8 * UN;             // warp units per tile
+
+    const EwParams& p;
+    int64_t lin0;
+    char* tbase[NARGS];           // operand pointers at the tile origin
+    uint32_t tiles_i, tiles_o, tiles, t;
+    int n_i, n_o, i0, o0, tile_i, tile_o;
+    int li[UN], lo[UN];           // lane's element offsets inside the tile, per unit
+    bool live;
+
+    B200_DEVICE explicit RegTileTiler(const EwParams& p_) : p(p_) {
+        n_i = int(p.shape[p.tile_axis]);
+        n_o = int(p.shape[p.ndim - 1]);
+        const int units_o = reg_tile_units_o(n_o, kUnitO, kUnits);
+        tile_o = units_o * kUnitO;
+        tile_i = (kUnits / units_o) * kUnitI;
+        tiles_i = static_cast<uint32_t>((n_i + tile_i - 1) / tile_i);
+        tiles_o = static_cast<uint32_t>((n_o + tile_o - 1) / tile_o);
+        tiles = static_cast<uint32_t>((p.size / (int64_t(n_i) * n_o)) * tiles_i * tiles_o);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int un = 0; un < UN; ++un) {
+            const int w = warp * UN + un;
+            li[un] = (w / units_o) * kUnitI + (lane % kLanesI) * kCH;
+            lo[un] = (w % units_o) * kUnitO + (lane / kLanesI) * kCH;
+        }
+        t = blockIdx.x;
+        live = t < tiles;
+        if (live) locate();
+    }
+    B200_DEVICE void locate() {
+        const int ax_i = p.tile_axis, ax_o = p.ndim - 1;
+        uint32_t b = t;
+        i0 = int(b % tiles_i) * tile_i;
+        b /= tiles_i;
+        o0 = int(b % tiles_o) * tile_o;
+        b /= tiles_o;
+        lin0 = int64_t(i0) * p.cstride[ax_i] + o0;
+#pragma unroll
+        for (int a = 0; a < NARGS; ++a)
+            tbase[a] = p.arg[a].ptr + int64_t(i0) * p.arg[a].strides[ax_i] + int64_t(o0) * p.arg[a].strides[ax_o];
+#pragma unroll 1
+        for (int d = p.ndim - 2; d >= 0; --d) {
+            if (d == ax_i) continue;
+            const uint32_t s = static_cast<uint32_t>(p.shape[d]);
+            const uint32_t r = b % s;
+            b /= s;
+            lin0 += int64_t(r) * p.cstride[d];
+#pragma unroll
+            for (int a = 0; a < NARGS; ++a) tbase[a] += int64_t(r) * p.arg[a].strides[d];
+        }
+    }
+    B200_DEVICE bool valid() const { return live; }
+    B200_DEVICE void next() {
+        t += gridDim.x;
+        live = t < tiles;
+        if (live) locate();
+    }
+    // One code path: the range test is one compare pair per 16-byte-square block, so a separate
+    // unpredicated instantiation would only double the code and the register allocation.
+    B200_DEVICE constexpr bool is_full() const { return false; }
+    // n_i and n_o are multiples of CH (planner), so a lane's block is wholly inside or wholly outside
+    B200_DEVICE bool unit_in(int un) const { return (i0 + li[un]) < n_i && (o0 + lo[un]) < n_o; }
+    template <bool FULL>
+    B200_DEVICE bool in_range(int u, int) const { return FULL || unit_in(u / kCH); }
+    B200_DEVICE int64_t index(int u, int k) const {
+        return lin0 + int64_t(li[u / kCH] + (u % kCH)) * p.cstride[p.tile_axis] + (lo[u / kCH] + k);
+    }
+
+    template <bool FULL, class T>
+    B200_DEVICE void load(int a, Pack<T, kV> (&r)[kU]) const {
+        static_assert(sizeof(T) == ESZ, "TILED_REG: every array operand has the tile's item size");
+        const uint32_t kind = uint32_t(SPEC >> (3 * a)) & 3u;
+        const bool bcast_i = (SPEC >> (3 * a + 2)) & 1u;
+        const int64_t s_o = (kind == 2) ? int64_t(sizeof(T)) : p.arg[a].strides[p.ndim - 1];
+        if (kind == 1) {
+            // unit-stride along I: CH vectors along I, one per row o .. o+CH-1
+#pragma unroll
+            for (int un = 0; un < UN; ++un) {
+                if (!FULL && !unit_in(un)) continue;
+                const char* b0 = tbase[a] + li[un] * int(sizeof(T)) + lo[un] * s_o;
+                Pack<T, kCH> q[kCH];
+#pragma unroll
+                for (int k = 0; k < kCH; ++k) load_pack(q[k], reinterpret_cast<const T*>(b0 + k * s_o));
+#pragma unroll
+                for (int x = 0; x < kCH; ++x)
+#pragma unroll
+                    for (int k = 0; k < kCH; ++k) r[un * kCH + x][k] = q[k][x];
+            }
+        } else {
+            const int64_t s_i = bcast_i ? 0 : p.arg[a].strides[p.tile_axis];
+#pragma unroll
+            for (int un = 0; un < UN; ++un) {
+                if (!FULL && !unit_in(un)) continue;
+                const char* b0 = tbase[a] + li[un] * s_i + lo[un] * s_o;
+#pragma unroll
+                for (int x = 0; x < (bcast_i ? 1 : kCH); ++x) {
+                    const char* q = b0 + x * s_i;
+                    if (kind == 2) {
+                        load_pack(r[un * kCH + x], reinterpret_cast<const T*>(q));
+                    } else if (s_o == 0) {
+                        const T v = *reinterpret_cast<const T*>(q);
+#pragma unroll
+                        for (int k = 0; k < kV; ++k) r[un * kCH + x][k] = v;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kV; ++k) r[un * kCH + x][k] = *reinterpret_cast<const T*>(q + k * s_o);
+                    }
+                }
+                if (bcast_i) {
+#pragma unroll
+                    for (int x = 1; x < kCH; ++x) r[un * kCH + x] = r[un * kCH];
+                }
+            }
+        }
+    }
+    template <bool FULL, class T>
+    B200_DEVICE void store(int a, const Pack<T, kV> (&r)[kU]) const {
+        const int64_t s_i = p.arg[a].strides[p.tile_axis];
+#pragma unroll
+        for (int un = 0; un < UN; ++un) {
+            if (!FULL && !unit_in(un)) continue;
+            char* b0 = tbase[a] + li[un] * s_i + lo[un] * int(sizeof(T));
+#pragma unroll
+            for (int x = 0; x < kCH; ++x) store_pack(reinterpret_cast<T*>(b0 + x * s_i), r[un * kCH + x]);
+        }
     }
 };
 

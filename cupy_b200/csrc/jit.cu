@@ -234,8 +234,24 @@ extern "C" __attribute__((visibility("default"))) int b200_jit_ew_launch(void* f
     if (st) return st;
     // block_size: threads per block the kernel was generated for; unroll is
     // encoded by the generator in the plan's reserved field
+    if (plan->variant == B200_EW_TILED_TMA) {
+        TileMaps tm;
+        st = build_tile_maps(plan, args, &tm);
+        if (st) return st;
+        int stages;
+        unsigned smem;
+        tma_ring(plan, &stages, &smem);
+        p.tma_stages = stages;
+        CUresult ra = d->FuncSetAttribute(static_cast<CUfunction>(function), 8 /*MAX_DYNAMIC_SHARED_SIZE_BYTES*/, 227 * 1024);
+        if (ra) return cu_fail(d, ra, "cuFuncSetAttribute");
+        const unsigned g = ew_grid(plan, 288, 1, di.sm_count);
+        void* targs[] = {&p, &raws, &tm};
+        CUresult rt = d->LaunchKernel(static_cast<CUfunction>(function), g, 1, 1, 288u, 1, 1, smem,
+                                      static_cast<CUstream>(stream), targs, nullptr);
+        return rt ? cu_fail(d, rt, "cuLaunchKernel") : 0;
+    }
     const int unroll = (plan->reserved & 0xff) ? int(plan->reserved & 0xff) : 1;
-    const int threads = plan->variant == B200_EW_TILED ? 256 : block_size;
+    const int threads = (plan->variant == B200_EW_TILED || plan->variant == B200_EW_TILED_REG) ? 256 : block_size;
     const unsigned grid = ew_grid(plan, threads, unroll, di.sm_count);
     void* kargs[] = {&p, &raws};
     CUresult r = d->LaunchKernel(static_cast<CUfunction>(function), grid, 1, 1, unsigned(threads), 1, 1, 0,

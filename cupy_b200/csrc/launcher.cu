@@ -15,6 +15,7 @@
 #include <mutex>
 
 #include "common.h"
+#include "tma_host.h"
 
 namespace b200 {
 
@@ -89,8 +90,86 @@ int fill_ew_params(const b200_ew_plan_t* plan, int nargs, const b200_operand_t* 
     return 0;
 }
 
+// ---- TILED_TMA geometry (mirrors TmaTileTiler in b200/elementwise.cuh)
+void tma_tile_geometry(const b200_ew_plan_t* plan, int* esz, int* tile_i, int* tile_o) {
+    const int e = int(plan->reserved >> 24);          // item size, set by the planner
+    *esz = e;
+    *tile_i = 128 / e;
+    *tile_o = 32 * (16 / e);
+}
+
+static int tma_nstaged(const b200_ew_plan_t* plan) { return __builtin_popcount(plan->staged_mask); }
+
+int tma_blocks_per_sm(const b200_ew_plan_t* plan) {
+    int e, ti, to;
+    tma_tile_geometry(plan, &e, &ti, &to);
+    const int tile_bytes = to * 128 * tma_nstaged(plan);
+    return tile_bytes * 3 * 2 + 4096 <= 200 * 1024 ? 2 : 1;
+}
+
+// ring depth and dynamic shared memory of one block
+void tma_ring(const b200_ew_plan_t* plan, int* stages, unsigned* smem_bytes) {
+    int e, ti, to;
+    tma_tile_geometry(plan, &e, &ti, &to);
+    const int tile_bytes = to * 128 * tma_nstaged(plan);
+    const int budget = 200 * 1024 / tma_blocks_per_sm(plan) - 2048;
+    int s = (plan->reserved & 0xff) ? int(plan->reserved & 0xff) : budget / tile_bytes;
+    s = std::max(2, std::min(s, 8));
+    while (s > 2 && s * tile_bytes > 220 * 1024) --s;
+    *stages = s;
+    *smem_bytes = unsigned(s * tile_bytes + 2048);
+}
+
+// One 5-D tensor map per staged operand: dims (tile axis, innermost loop dim,
+// then the batch dims innermost-first), box = one tile, 128-byte swizzle.
+int build_tile_maps(const b200_ew_plan_t* plan, const b200_operand_t* args, TileMaps* out) {
+    int e, ti, to;
+    tma_tile_geometry(plan, &e, &ti, &to);
+    const int nd = plan->ndim, last = nd - 1, ax = plan->tile_axis;
+    int slot = 0;
+    for (int a = 0; a < plan->nargs; ++a) {
+        if (!((plan->staged_mask >> a) & 1u)) continue;
+        uint64_t dims[5] = {1, 1, 1, 1, 1}, strides[4] = {16, 16, 16, 16};
+        uint32_t box[5] = {uint32_t(ti), uint32_t(to), 1, 1, 1};
+        dims[0] = uint64_t(plan->shape[ax]);
+        dims[1] = uint64_t(plan->shape[last]);
+        strides[0] = uint64_t(plan->strides[a][last]);
+        int n = 2;
+        for (int d = nd - 2; d >= 0; --d) {
+            if (d == ax) continue;
+            dims[n] = uint64_t(plan->shape[d]);
+            strides[n - 1] = uint64_t(plan->strides[a][d]);
+            ++n;
+        }
+        static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "tensor map blob size");
+        int st = make_tensor_map(reinterpret_cast<CUtensorMap*>(&out->m[slot]), e, args[a].data, 5, dims, strides, box,
+                                 CU_TENSOR_MAP_SWIZZLE_128B);
+        if (st) return st;
+        ++slot;
+    }
+    return 0;
+}
+
 unsigned ew_grid(const b200_ew_plan_t* plan, int threads, int unroll, int sm_count) {
     int64_t blocks;
+    if (plan->variant == B200_EW_TILED_TMA) {
+        int esz, ti, to;
+        tma_tile_geometry(plan, &esz, &ti, &to);
+        const int64_t ni = plan->shape[plan->tile_axis], no = plan->shape[plan->ndim - 1];
+        blocks = ((ni + ti - 1) / ti) * ((no + to - 1) / to) * (plan->size / (ni * no));
+        const int per_sm = ((plan->reserved >> 8) & 0xffff) ? int((plan->reserved >> 8) & 0xffff) : tma_blocks_per_sm(plan);
+        return unsigned(std::max<int64_t>(1, std::min<int64_t>(blocks, int64_t(sm_count) * per_sm)));
+    }
+    if (plan->variant == B200_EW_TILED_REG) {
+        // mirrors RegTileTiler: 8*UN warp units of (128 B along I) x (64 B along O), O first
+        const int e = int(plan->reserved >> 24), ch = 16 / e, un = (plan->reserved & 0xff) ? int(plan->reserved & 0xff) : reg_tile_unroll(e), units = 8 * un;
+        const int64_t ni = plan->shape[plan->tile_axis], no = plan->shape[plan->ndim - 1];
+        const int units_o = reg_tile_units_o(no, 4 * ch, units);
+        const int64_t to = int64_t(units_o) * 4 * ch, ti = int64_t(units / units_o) * 8 * ch;
+        blocks = ((ni + ti - 1) / ti) * ((no + to - 1) / to) * (plan->size / (ni * no));
+        const int per_sm = ((plan->reserved >> 8) & 0xffff) ? int((plan->reserved >> 8) & 0xffff) : 32;
+        return unsigned(std::max<int64_t>(1, std::min<int64_t>(blocks, int64_t(sm_count) * per_sm)));
+    }
     if (plan->variant == B200_EW_TILED) {
         const int64_t ni = plan->shape[plan->tile_axis], no = plan->shape[plan->ndim - 1];
         blocks = ((ni + 31) / 32) * ((no + 31) / 32) * (plan->size / (ni * no));
@@ -253,6 +332,37 @@ extern "C" __attribute__((visibility("default"))) int b200_ew_plan(int nargs, co
             plan->tile_axis = axis;
             plan->staged_mask = mask;
             plan->vec = 1;
+            // Vector forms (TILED_REG by default, TILED_TMA on request): one item size (2/4/8 B)
+            // across the array operands and 16-byte alignment of every base and every stride that
+            // a vector access (or a tensor map) steps by; both tile extents multiples of 16/item.
+            const char* mode_env = getenv("B200_EW_TILED_MODE");
+            const int mode = !mode_env ? 0 : !strcmp(mode_env, "tma") ? 1 : !strcmp(mode_env, "smem") ? 2 : 0;
+            int esz = 0;
+            bool vecok = mask != 0 && mode != 2;
+            bool tma = nd <= 5 && __builtin_popcount(mask) <= kMaxStaged;
+            for (int a = 0; a < nargs && vecok; ++a) {
+                if (!is_array(args[a])) continue;
+                const int isz = dtype_size(args[a].dtype);
+                if (esz == 0) esz = isz;
+                if (isz != esz || (isz != 2 && isz != 4 && isz != 8)) { vecok = false; break; }
+                const bool staged = (mask >> a) & 1u;
+                const bool unit = st[a][last] == isz;
+                if (!staged && !unit) continue;              // scalar accesses: no alignment needed
+                if (reinterpret_cast<uintptr_t>(args[a].data) % 16) vecok = false;
+                for (int d = 0; d < nd && vecok; ++d) {
+                    if (staged ? d == axis : d == last) continue;
+                    if (st[a][d] % 16) vecok = false;
+                    if (staged && (st[a][d] <= 0 || st[a][d] >= (int64_t(1) << 40))) tma = false;
+                }
+            }
+            for (int d = 0; d < nd; ++d)
+                if (shape[d] >= (int64_t(1) << 31)) vecok = false;
+            if (vecok && esz && shape[last] % (16 / esz) == 0 && shape[axis] % (16 / esz) == 0 &&
+                size / (16 / esz) / (16 / esz) < (int64_t(1) << 31)) {
+                plan->variant = (mode == 1 && tma) ? B200_EW_TILED_TMA : B200_EW_TILED_REG;
+                plan->vec = 16 / esz;
+                plan->reserved = uint32_t(esz) << 24;
+            }
             return 0;
         }
     }

@@ -115,6 +115,10 @@ typedef struct b200_operand {
 #define B200_EW_FLAT     0   /* every array operand is dense with the same layout: 1-D, 128-bit vector access */
 #define B200_EW_ROWWISE  1   /* N-D strided / broadcast: vectors along the innermost dim, one index decomposition per vector */
 #define B200_EW_TILED    2   /* some input is unit-stride along another dim: 32x32 shared-memory tile transpose */
+#define B200_EW_TILED_TMA 3  /* same call shape, equal item sizes, 16-byte aligned: TMA-pipelined swizzled tiles (A/B knob
+                                B200_EW_TILED_MODE=tma; tensor copies are translation-bound on 4 MB-strided rows) */
+#define B200_EW_TILED_REG 4  /* same conditions: register-block transpose (16-byte vectors along both dims, no shared
+                                memory) -- the default for transposing calls */
 
 typedef struct b200_ew_plan {
     int32_t  variant;                  /* B200_EW_* */

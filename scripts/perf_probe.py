@@ -6,7 +6,7 @@ import torch
 import cupy_b200 as cp
 from cupy_b200._core import _kernel
 
-PEAK = 6545.9
+PEAK = 6546.9
 
 
 def timeit(f, iters=20, warm=3):
@@ -94,6 +94,54 @@ def main():
         fused = cp.ElementwiseKernel('T x, T v', 'T z', 'z = exp(x) + v', 'expadd')
         report('fused exp(x^T)+v ElementwiseKernel', 8 * nel, lambda: fused(xt, v, out), iters=10)
         report('copy transposed (ascontiguous)', 8 * nel, lambda: cp.elementwise_copy(xt, out), iters=10)
+        k1 = cp.ElementwiseKernel('T x', 'T z', 'z = exp(x)', 'jit_exp')
+        k2 = cp.ElementwiseKernel('T x, T v', 'T z', 'z = x + v', 'jit_addv')
+        k3 = cp.ElementwiseKernel('T x, T v', 'T z', 'z = __expf(x) + v', 'jit_fastexp_addv')
+        for un, mb in ((0, 0), (1, 4), (1, 5), (2, 3)):
+            _kernel.tunables['reg_min_blocks'] = mb
+            _kernel.tunables['reg_unroll'] = un
+            report('  JIT exp(x^T) unroll=%d min_blocks=%d' % (un, mb), 8 * nel, lambda: k1(xt, out), iters=10)
+            report('  JIT x^T + v unroll=%d min_blocks=%d' % (un, mb), 8 * nel, lambda: k2(xt, v, out), iters=10)
+            report('  JIT __expf(x^T) + v unroll=%d min_blocks=%d' % (un, mb), 8 * nel, lambda: k3(xt, v, out), iters=10)
+            report('  JIT exp(x^T) + v unroll=%d min_blocks=%d' % (un, mb), 8 * nel, lambda: fused(xt, v, out), iters=10)
+        _kernel.tunables['reg_min_blocks'] = 0
+        _kernel.tunables['reg_unroll'] = 0
+        import os
+        os.environ['B200_EW_TILED_MODE'] = 'reg'
+        for mode in ():
+            os.environ['B200_EW_TILED_MODE'] = mode
+            report('  [%s] exp(x^T)' % mode, 8 * nel, lambda: cp.exp(xt, out=tmp), iters=10)
+            report('  [%s] fused exp(x^T)+v' % mode, 8 * nel, lambda: fused(xt, v, out), iters=10)
+            report('  [%s] copy transposed' % mode, 8 * nel, lambda: cp.elementwise_copy(xt, out), iters=10)
+        del os.environ['B200_EW_TILED_MODE']
+        if 'sweep2' in which:
+            for bps in (4, 8, 16, 32, 64):
+                _kernel.tunables['blocks_per_sm'] = bps
+                report('  [reg] fused blocks/SM=%d' % bps, 8 * nel, lambda: fused(xt, v, out), iters=10)
+            _kernel.tunables['blocks_per_sm'] = 0
+            for un in (1, 2, 4):
+                for mb in (1, 2, 3, 4):
+                    _kernel.tunables['reg_min_blocks'] = mb
+                    _kernel.tunables['reg_unroll'] = un
+                    report('  [reg] fused unroll=%d min_blocks=%d' % (un, mb), 8 * nel, lambda: fused(xt, v, out), iters=10)
+            _kernel.tunables['reg_min_blocks'] = 0
+            _kernel.tunables['reg_unroll'] = 0
+        h = cp.from_torch(randn((256, 1024, 1024), torch.float16)).transpose(2, 1, 0)
+        ho = cp.empty((1024, 1024, 256), np.float16)
+        report('copy transposed float16', 4 * nel, lambda: cp.elementwise_copy(h, ho), iters=10)
+        del h, ho
+        sq = cp.from_torch(randn((16384, 16384), torch.float32))
+        sqo = cp.empty((16384, 16384), np.float32)
+        report('2-D transpose 16384^2 f32', 8 * (1 << 28), lambda: cp.elementwise_copy(sq.T, sqo), iters=10)
+        report('2-D x^T + y 16384^2 f32', 12 * (1 << 28), lambda: cp.add(sq.T, sqo, out=sqo), iters=10)
+        for un in (1, 2):
+            for mb in (1, 2, 3, 4):
+                _kernel.tunables['reg_min_blocks'] = mb
+                _kernel.tunables['reg_unroll'] = un
+                report('  2-D x^T + y unroll=%d min_blocks=%d' % (un, mb), 12 * (1 << 28), lambda: cp.add(sq.T, sqo, out=sqo), iters=10)
+        _kernel.tunables['reg_min_blocks'] = 0
+        _kernel.tunables['reg_unroll'] = 0
+        del sq, sqo
         del base, xt, out, tmp
         torch.cuda.empty_cache()
     if 'scan' in which:

@@ -99,14 +99,28 @@ def test_plan_transposed_input_is_tiled():
                   _operand(0x200000, F32, shape, (0, 0, 4)),
                   _operand(0x300000, F32, shape, (1048576, 1024, 4), out=True)])
     assert s == 0
-    assert p.variant == _lib.EW_TILED and p.tile_axis == 0 and p.staged_mask == 0b001 and p.ndim == 3
+    # equal item sizes, 16-byte aligned bases and strides -> the register-block tiler
+    assert p.variant == _lib.EW_TILED_REG and p.tile_axis == 0 and p.staged_mask == 0b001 and p.ndim == 3
+    assert p.vec == 4 and (p.reserved >> 24) == 4
+    # a misaligned base (or mixed item sizes) keeps the plain shared-memory tile
+    s, p = _plan([_operand(0x100004, F32, shape, (4, 4096, 4194304)),
+                  _operand(0x200000, F32, shape, (0, 0, 4)),
+                  _operand(0x300000, F32, shape, (1048576, 1024, 4), out=True)])
+    assert s == 0 and p.variant == _lib.EW_TILED and p.staged_mask == 0b001
+    s, p = _plan([_operand(0x100000, F32, shape, (4, 4096, 4194304)),
+                  _operand(0x300000, _lib.TYPE_FLOAT64, shape, (2097152, 2048, 8), out=True)])
+    assert s == 0 and p.variant == _lib.EW_TILED
+    # innermost extent not a multiple of the vector width
+    s, p = _plan([_operand(0x100000, F32, (64, 30), (4, 256)),
+                  _operand(0x300000, F32, (64, 30), (120, 4), out=True)])
+    assert s == 0 and p.variant == _lib.EW_TILED
 
 
 def test_plan_2d_transpose_collapse_and_64bit():
     # 2-D transposed view: no collapse possible, tiled on axis 0
     s, p = _plan([_operand(0x1000, F32, (4096, 4096), (4, 16384)),
                   _operand(0x8000000, F32, (4096, 4096), (16384, 4), out=True)])
-    assert p.variant == _lib.EW_TILED and p.idx32 == 1
+    assert p.variant == _lib.EW_TILED_REG and p.idx32 == 1
     # > 2^31 elements -> 64-bit indexing
     s, p = _plan([_operand(0x1000, _lib.TYPE_INT8, (1 << 32,), (1,)), _operand(0x1000, _lib.TYPE_INT8, (1 << 32,), (1,), out=True)])
     assert p.variant == _lib.EW_FLAT and p.idx32 == 0 and p.size == 1 << 32

@@ -191,11 +191,11 @@ def test_classification_of_config_shapes(dry):
     xt = cp.empty((64, 128, 256), 'f').transpose(2, 1, 0)
     v = cp.empty((64,), 'f')
     cp.exp(xt)
-    assert dry[-1]['variant'] == _lib.EW_TILED and dry[-1]['tile_axis'] == 0 and dry[-1]['staged_mask'] == 1
+    assert dry[-1]['variant'] == _lib.EW_TILED_REG and dry[-1]['tile_axis'] == 0 and dry[-1]['staged_mask'] == 1
     cp.add(cp.empty((256, 128, 64), 'f'), v)
     assert dry[-1]['variant'] == _lib.EW_ROWWISE and dry[-1]['vec'] == 4 and dry[-1]['ndim'] == 2
     cp.ElementwiseKernel('T x, T v', 'T z', 'z = exp(x) + v', 'fused')(xt, v)
-    assert dry[-1]['variant'] == _lib.EW_TILED
+    assert dry[-1]['variant'] == _lib.EW_TILED_REG and 'RegTileTiler<3, 4, 1, 177ull>' in dry[-1]['source']
     h = cp.empty((n,), 'e')
     cp.add(h, h)
     assert dry[-1]['variant'] == _lib.EW_FLAT and dry[-1]['vec'] == 8
@@ -327,3 +327,16 @@ def test_views_match_numpy_strides(dry):
     with pytest.raises(ValueError):
         a.reshape(7, -1)
     assert cp.may_share_bounds(a[0], a[0:1]) and not cp.may_share_bounds(a[0], a[1])
+
+
+def test_codegen_skips_the_load_of_write_first_outputs(dry):
+    from cupy_b200._core._codegen import writes_first as w
+    assert w('z = exp(x) + v', 'z') and w('z = a * x + y', 'z') and w('z = x > 0 ? x : 0', 'z')
+    assert w('T t = x * 2; z = t; w = z + 1', 'z') and w('T t = x * 2; z = t; w = z + 1', 'w')
+    for op in ('z += x', 'y = z; z = x', 'if (x > 0) z = x', 'z == x', 'zz = 1', 'for (int k = 0; k < 2; ++k) { z = x; }'):
+        assert not w(op, 'z'), op
+    x = cp.empty((1 << 16,), 'f')
+    cp.ElementwiseKernel('T x', 'T z', 'z = x * 2', 'wf_a')(x)
+    assert 'load<_FULL>(1' not in dry[-1]['source']
+    cp.ElementwiseKernel('T x', 'T z', 'z += x', 'wf_b')(x, cp.empty((1 << 16,), 'f'))
+    assert 'load<_FULL>(1' in dry[-1]['source']
