@@ -260,6 +260,39 @@ def _var(a, axis=None, dtype=None, out=None, ddof=0, keepdims=False):
     return out.astype(dtype_out, copy=False)
 
 
+def moments(a):
+    """(mean, M2) of all elements of a dense array in ONE pass (B200_OP_MOMENTS): a 2-element
+    array of the accumulation float type (float32 for float16/float32 inputs, float64
+    otherwise).  M2 = sum((x - mean)^2); var = M2 / (n - ddof).  This is what a sharded
+    variance exchanges (cupy_b200.distributed.sharded_var); the reference needs two passes
+    (cupy/_core/_routines_statistics.pyx:556-600)."""
+    import ctypes
+    from cupy_b200._core import _reduction, _workspace, _dryrun
+    from cupy_b200._core._kernel import current_stream_ptr
+    if a.size == 0:
+        raise ValueError('moments of an empty array')
+    layout = _reduction._classify(a.shape, a.strides, a.dtype.itemsize, tuple(range(a.ndim)), (), False)
+    if layout.kind != _lib.RED_FULL:
+        a = a.copy()
+        layout = _reduction._classify(a.shape, a.strides, a.dtype.itemsize, tuple(range(a.ndim)), (), False)
+    ftype = numpy.dtype('float32') if a.dtype in (numpy.dtype('float16'), numpy.dtype('float32')) else numpy.dtype('float64')
+    out = ndarray((2,), ftype)
+    desc = _lib.ReduceDesc(_lib.OP_MOMENTS, layout.kind, _scalar.dtype_id(a.dtype), _scalar.dtype_id(ftype),
+                           layout.batch, layout.n_reduce, layout.n_out, 0.0)
+    if not _lib.lib.b200_reduce_supported(ctypes.byref(desc)):
+        raise NotImplementedError('moments: dtype %s has no prebuilt kernel' % a.dtype)
+    if _dryrun.enabled:
+        _dryrun.record('prebuilt_reduce', name='cupy_moments', layout=layout.kind, batch=layout.batch,
+                       n_reduce=layout.n_reduce, n_out=layout.n_out)
+        return out
+    st = current_stream_ptr()
+    need = ctypes.c_size_t()
+    _lib.check(_lib.lib.b200_reduce_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
+    ws_ptr, ws_bytes = _workspace.get(need.value, st)
+    _lib.check(_lib.lib.b200_reduce_run(ctypes.byref(desc), a.ptr, out.ptr, ws_ptr, ws_bytes, st))
+    return out
+
+
 def _out_shape(shape, reduce_axis, out_axis, keepdims):
     from cupy_b200._core._reduction import _get_out_shape
     return _get_out_shape(shape, reduce_axis, out_axis, keepdims)

@@ -25,7 +25,7 @@ TYPE_INT8, TYPE_UINT8, TYPE_INT16, TYPE_UINT16, TYPE_INT32, TYPE_UINT32, \
 
 # op codes (== cupy/cuda/cupy_cub.h:4-11, then extensions)
 OP_SUM, OP_MIN, OP_MAX, OP_ARGMIN, OP_ARGMAX, OP_CUMSUM, OP_CUMPROD, OP_PROD, \
-    OP_MEAN, OP_VAR = range(10)
+    OP_MEAN, OP_VAR, OP_MOMENTS = range(11)
 
 OK, E_INVALID, E_UNSUPPORTED, E_WORKSPACE, E_NOLIB, E_COMPILE = 0, -1, -2, -3, -4, -5
 

@@ -297,10 +297,17 @@ struct ThreadAcc<ArgOp<In, Index, kMax>, U, V, true> : ArgLanes<In, Index, kMax,
 // through Chan's pairwise merge.  F = float (fp16/fp32 inputs) or double.
 template <class F>
 struct Moments { F n, mean, m2; };
+// what B200_OP_MOMENTS writes per output element: the pair a caller needs to merge shards
+template <class F>
+struct MeanM2 { F mean, m2; };
+// kMode of MomentsOp
+constexpr int kMomMean = 0, kMomVar = 1, kMomPair = 2;
+template <class F, class Out, int kMode> struct moments_out { typedef Out type; };
+template <class F, class Out> struct moments_out<F, Out, kMomPair> { typedef MeanM2<F> type; };
 
-template <class In, class F, class Out, bool kVar>
+template <class In, class F, class Out, int kMode>
 struct MomentsOp {
-    typedef In in_t; typedef Moments<F> acc_t; typedef Out out_t; typedef long long index_t;
+    typedef In in_t; typedef Moments<F> acc_t; typedef typename moments_out<F, Out, kMode>::type out_t; typedef long long index_t;
     struct ctx_t { F rcp; F cnt; };
     static constexpr bool kWideIndex = false;
     F ddof;
@@ -329,10 +336,15 @@ struct MomentsOp {
         return r;
     }
     B200_DEVICE out_t post(const acc_t& a, long long n) const {
-        if (!kVar) return static_cast<out_t>(a.mean);
-        const F div = F(n) - ddof;
-        // alpha = 1/max(n-ddof,0), NaN when empty: cupy/_core/_routines_statistics.pyx:585-586
-        return static_cast<out_t>(div > F(0) ? a.m2 / div : (a.m2 / F(0)) * F(0));
+        if constexpr (kMode == kMomPair) {
+            out_t r; r.mean = a.mean; r.m2 = a.m2; return r;
+        } else if constexpr (kMode == kMomMean) {
+            return static_cast<out_t>(a.mean);
+        } else {
+            const F div = F(n) - ddof;
+            // alpha = 1/max(n-ddof,0), NaN when empty: cupy/_core/_routines_statistics.pyx:585-586
+            return static_cast<out_t>(div > F(0) ? a.m2 / div : (a.m2 / F(0)) * F(0));
+        }
     }
 };
 
@@ -346,9 +358,9 @@ struct MomentsOp {
 // whatever U is -- so U can follow the memory system (bytes in flight), not the register file.
 // The very first batch is centred on its own first element.
 // ---------------------------------------------------------------------------
-template <class In, class F, class Out, bool kVar, int U, int V>
+template <class In, class F, class Out, int kMode, int U, int V>
 struct MomentLanes {
-    typedef MomentsOp<In, F, Out, kVar> Op;
+    typedef MomentsOp<In, F, Out, kMode> Op;
     typedef typename Op::acc_t acc_t;
     typedef typename Op::index_t index_t;
     const Op& op;
@@ -400,12 +412,12 @@ struct MomentLanes {
     }
 };
 
-template <class In, class F, class Out, bool kVar>
-struct fast_lanes<MomentsOp<In, F, Out, kVar>> { static constexpr bool value = true; };
+template <class In, class F, class Out, int kMode>
+struct fast_lanes<MomentsOp<In, F, Out, kMode>> { static constexpr bool value = true; };
 
-template <class In, class F, class Out, bool kVar, int U, int V>
-struct ThreadAcc<MomentsOp<In, F, Out, kVar>, U, V, true> : MomentLanes<In, F, Out, kVar, U, V> {
-    B200_DEVICE explicit ThreadAcc(const MomentsOp<In, F, Out, kVar>& op_) : MomentLanes<In, F, Out, kVar, U, V>(op_) {}
+template <class In, class F, class Out, int kMode, int U, int V>
+struct ThreadAcc<MomentsOp<In, F, Out, kMode>, U, V, true> : MomentLanes<In, F, Out, kMode, U, V> {
+    B200_DEVICE explicit ThreadAcc(const MomentsOp<In, F, Out, kMode>& op_) : MomentLanes<In, F, Out, kMode, U, V>(op_) {}
 };
 
 }  // namespace b200

@@ -257,9 +257,18 @@ static int run_for_type(const b200_reduce_desc_t* d, const void* x, void* y, voi
         case B200_OP_VAR: {
             typedef typename mom_float<T>::type F; typedef typename mom_out<T>::type O;
             B200_REQUIRE_OUT(O);
-            MomentsOp<T, F, O, true> op;
+            MomentsOp<T, F, O, kMomVar> op;
             op.ddof = F(d->param);
-            return run_typed<MomentsOp<T, F, O, true>, FV>(op, d, x, y, ws, wsb, s, query, need);
+            return run_typed<MomentsOp<T, F, O, kMomVar>, FV>(op, d, x, y, ws, wsb, s, query, need);
+        }
+        case B200_OP_MOMENTS: {
+            // y holds (mean, M2) pairs of the accumulation float type: 2 * n_out elements of F
+            typedef typename mom_float<T>::type F;
+            B200_REQUIRE_OUT(F);
+            if (d->layout != B200_RED_FULL) return fail(B200_E_UNSUPPORTED, "B200_OP_MOMENTS is a full reduction");
+            MomentsOp<T, F, F, kMomPair> op;
+            op.ddof = F(0);
+            return run_typed<MomentsOp<T, F, F, kMomPair>, FV>(op, d, x, y, ws, wsb, s, query, need);
         }
         default:
             return fail(B200_E_INVALID, "op code %d is not a reduction", d->op);

@@ -123,18 +123,16 @@ def combine_moments(counts, means, m2s):
 def sharded_var(x_local, comm, ddof=0):
     """Variance of a 1-D array sharded over the ranks (the reference has no
     distributed var, cupyx/distributed/array/_array.py:744-747; the oracle is
-    numpy.var of the gathered array).  Per rank (n, mean, M2) in float64, one
-    all-gather of 3 doubles, Chan merge in rank order."""
+    numpy.var of the gathered array).  ONE pass over the shard gives (mean, M2)
+    (B200_OP_MOMENTS), then one all-gather of 3 doubles per rank and a Chan merge in
+    rank order, so every rank computes the bit-identical result."""
+    from cupy_b200._core._routines_statistics import moments
     n_local = x_local.size
-    mean = x_local.mean()
-    var = x_local.var()
-    dev = mean.to_torch().device
-    loc = torch.stack([torch.tensor(float(n_local), dtype=torch.float64, device=dev),
-                       mean.to_torch().double().reshape(()),
-                       var.to_torch().double().reshape(()) * n_local])
+    mm = moments(x_local).to_torch().double()
+    loc = torch.cat([torch.full((1,), float(n_local), dtype=torch.float64, device=mm.device), mm])
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world > 1:
-        allv = torch.empty(world * 3, dtype=torch.float64, device=dev)
+        allv = torch.empty(world * 3, dtype=torch.float64, device=mm.device)
         dist.all_gather_into_tensor(allv, loc)
         allv = allv.reshape(world, 3)
     else:

@@ -81,6 +81,10 @@ extern "C" {
  * cupy/_core/_routines_statistics.pyx:611-655) */
 #define B200_OP_MEAN     8
 #define B200_OP_VAR      9    /* param = ddof; single pass Welford/Chan */
+#define B200_OP_MOMENTS  10   /* full reductions only: y = (mean, M2) in the accumulation float type (float for
+                                 fp16/fp32 inputs, double otherwise) -- what a caller needs to merge shards
+                                 (Chan) without a second pass; the reference has no counterpart (two passes,
+                                 cupy/_core/_routines_statistics.pyx:556-600) */
 
 /* ---- status codes */
 #define B200_OK               0

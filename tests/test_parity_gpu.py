@@ -435,3 +435,21 @@ def test_scan_variants(cp):
     np.testing.assert_array_equal(mis.cumsum().get(), np.arange(1, 1001).cumsum())
     np.testing.assert_array_equal(cp.add.accumulate(cp.asarray(p)).get(), np.add.accumulate(p))
     np.testing.assert_array_equal(cp.add.reduce(d, axis=1).get(), np.add.reduce(a, axis=1))
+
+
+@pytest.mark.parametrize('dt', ['float32', 'float16', 'float64', 'int32', 'int64'])
+@pytest.mark.parametrize('n', [1, 7, 4096, 1 << 20, (1 << 22) + 3])
+def test_moments_single_pass_mean_m2(cp, n, dt):
+    """B200_OP_MOMENTS (what sharded_var exchanges): (mean, M2) of one pass vs float64 NumPy."""
+    from cupy_b200._core._routines_statistics import moments
+    a = rnd((n,), dt)
+    got = moments(cp.asarray(a)).get()
+    want_dt = np.float32 if np.dtype(dt) in (np.dtype('float16'), np.dtype('float32')) else np.float64
+    assert got.dtype == want_dt and got.shape == (2,)
+    a64 = a.astype(np.float64)
+    tol = 1e-5 if want_dt == np.float32 else 1e-12
+    np.testing.assert_allclose(got[0], a64.mean(), rtol=tol, atol=tol * np.abs(a64).mean())
+    np.testing.assert_allclose(got[1], ((a64 - a64.mean()) ** 2).sum(), rtol=tol * 10, atol=1e-30)
+    # 2-D dense input is the same full reduction
+    if n == 4096:
+        np.testing.assert_allclose(moments(cp.asarray(a.reshape(64, 64))).get(), got, rtol=1e-6)
