@@ -260,10 +260,10 @@ def _var(a, axis=None, dtype=None, out=None, ddof=0, keepdims=False):
     return out.astype(dtype_out, copy=False)
 
 
-def moments(a):
-    """(mean, M2) of all elements of a dense array in ONE pass (B200_OP_MOMENTS): a 2-element
-    array of the accumulation float type (float32 for float16/float32 inputs, float64
-    otherwise).  M2 = sum((x - mean)^2); var = M2 / (n - ddof).  This is what a sharded
+def moments(a, out=None):
+    """(n, mean, M2) of all elements of a dense array in ONE pass (B200_OP_MOMENTS): three
+    float64 values (accumulated in float32 for float16/float32 inputs, float64 otherwise).
+    M2 = sum((x - mean)^2); var = M2 / (n - ddof).  This is what a sharded
     variance exchanges (cupy_b200.distributed.sharded_var); the reference needs two passes
     (cupy/_core/_routines_statistics.pyx:556-600)."""
     import ctypes
@@ -275,8 +275,8 @@ def moments(a):
     if layout.kind != _lib.RED_FULL:
         a = a.copy()
         layout = _reduction._classify(a.shape, a.strides, a.dtype.itemsize, tuple(range(a.ndim)), (), False)
-    ftype = numpy.dtype('float32') if a.dtype in (numpy.dtype('float16'), numpy.dtype('float32')) else numpy.dtype('float64')
-    out = ndarray((2,), ftype)
+    ftype = numpy.dtype('float64')
+    out = ndarray((3,), ftype) if out is None else out
     desc = _lib.ReduceDesc(_lib.OP_MOMENTS, layout.kind, _scalar.dtype_id(a.dtype), _scalar.dtype_id(ftype),
                            layout.batch, layout.n_reduce, layout.n_out, 0.0)
     if not _lib.lib.b200_reduce_supported(ctypes.byref(desc)):

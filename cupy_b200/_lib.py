@@ -108,6 +108,7 @@ _EXPORTS = {
     'b200_reduce_supported': (c_int, [POINTER(ReduceDesc)]),
     'b200_reduce_workspace_bytes': (c_int, [POINTER(ReduceDesc), POINTER(c_size_t)]),
     'b200_reduce_run': (c_int, [POINTER(ReduceDesc), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'b200_moments_merge': (c_int, [c_void_p, c_int, c_double, c_void_p, c_void_p]),
     'b200_scan_supported': (c_int, [c_int, c_int, c_int]),
     'b200_scan_workspace_bytes': (c_int, [c_int64, c_int, POINTER(c_size_t)]),
     'b200_scan_run': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),

@@ -297,13 +297,13 @@ struct ThreadAcc<ArgOp<In, Index, kMax>, U, V, true> : ArgLanes<In, Index, kMax,
 // through Chan's pairwise merge.  F = float (fp16/fp32 inputs) or double.
 template <class F>
 struct Moments { F n, mean, m2; };
-// what B200_OP_MOMENTS writes per output element: the pair a caller needs to merge shards
-template <class F>
-struct MeanM2 { F mean, m2; };
+// what B200_OP_MOMENTS writes per output element: the triple a caller needs to merge shards,
+// always in double so that it can go straight into an all-gather
+struct MomentTriple { double n, mean, m2; };
 // kMode of MomentsOp
 constexpr int kMomMean = 0, kMomVar = 1, kMomPair = 2;
 template <class F, class Out, int kMode> struct moments_out { typedef Out type; };
-template <class F, class Out> struct moments_out<F, Out, kMomPair> { typedef MeanM2<F> type; };
+template <class F, class Out> struct moments_out<F, Out, kMomPair> { typedef MomentTriple type; };
 
 template <class In, class F, class Out, int kMode>
 struct MomentsOp {
@@ -337,7 +337,7 @@ struct MomentsOp {
     }
     B200_DEVICE out_t post(const acc_t& a, long long n) const {
         if constexpr (kMode == kMomPair) {
-            out_t r; r.mean = a.mean; r.m2 = a.m2; return r;
+            out_t r; r.n = double(n); r.mean = double(a.mean); r.m2 = double(a.m2); return r;
         } else if constexpr (kMode == kMomMean) {
             return static_cast<out_t>(a.mean);
         } else {

@@ -31,9 +31,38 @@ static int dispatch(const b200_reduce_desc_t* d, const void* x, void* y, void* w
     }
 }
 
+// Chan merge of `count` (n, mean, M2) triples in index order (rank order: every rank of a
+// sharded variance computes the bit-identical result); one thread, the data is 24*count bytes.
+__global__ void moments_merge_kernel(const double* __restrict__ t, int count, double ddof, double* __restrict__ out) {
+    double n = t[0], mean = t[1], m2 = t[2];
+    for (int k = 1; k < count; ++k) {
+        const double nb = t[3 * k], mb = t[3 * k + 1], m2b = t[3 * k + 2];
+        const double tot = n + nb;
+        if (nb == 0.0) continue;
+        if (n == 0.0) { n = nb; mean = mb; m2 = m2b; continue; }
+        const double d = mb - mean, w = nb / tot;
+        mean += d * w;
+        m2 += m2b + d * d * n * w;
+        n = tot;
+    }
+    const double div = n - ddof;
+    out[0] = div > 0.0 ? m2 / div : (m2 / 0.0) * 0.0;
+    out[1] = mean;
+    out[2] = n;
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" __attribute__((visibility("default"))) int b200_moments_merge(const double* triples, int count, double ddof,
+                                                                          double* out, void* stream) {
+    if (!triples || !out) return fail(B200_E_INVALID, "null data pointer");
+    if (count < 1) return fail(B200_E_INVALID, "moments_merge: count %d", count);
+    moments_merge_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(triples, count, ddof, out);
+    B200_CUDA_TRY(cudaPeekAtLastError());
+    return 0;
+}
 
 extern "C" __attribute__((visibility("default"))) int b200_reduce_workspace_bytes(const b200_reduce_desc_t* d, size_t* bytes) {
     if (!bytes) return fail(B200_E_INVALID, "null argument");

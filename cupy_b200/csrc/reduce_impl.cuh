@@ -262,9 +262,9 @@ static int run_for_type(const b200_reduce_desc_t* d, const void* x, void* y, voi
             return run_typed<MomentsOp<T, F, O, kMomVar>, FV>(op, d, x, y, ws, wsb, s, query, need);
         }
         case B200_OP_MOMENTS: {
-            // y holds (mean, M2) pairs of the accumulation float type: 2 * n_out elements of F
+            // y holds one (n, mean, M2) triple of doubles
             typedef typename mom_float<T>::type F;
-            B200_REQUIRE_OUT(F);
+            B200_REQUIRE_OUT(double);
             if (d->layout != B200_RED_FULL) return fail(B200_E_UNSUPPORTED, "B200_OP_MOMENTS is a full reduction");
             MomentsOp<T, F, F, kMomPair> op;
             op.ddof = F(0);

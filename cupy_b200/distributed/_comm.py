@@ -126,17 +126,18 @@ def sharded_var(x_local, comm, ddof=0):
     numpy.var of the gathered array).  ONE pass over the shard gives (mean, M2)
     (B200_OP_MOMENTS), then one all-gather of 3 doubles per rank and a Chan merge in
     rank order, so every rank computes the bit-identical result."""
+    import ctypes
+    import numpy
+    from cupy_b200 import _lib
+    from cupy_b200._core._ndarray import ndarray
+    from cupy_b200._core._kernel import current_stream_ptr
     from cupy_b200._core._routines_statistics import moments
-    n_local = x_local.size
-    mm = moments(x_local).to_torch().double()
-    loc = torch.cat([torch.full((1,), float(n_local), dtype=torch.float64, device=mm.device), mm])
     world = dist.get_world_size() if dist.is_initialized() else 1
+    buf = ndarray((world + 1, 3), numpy.float64)         # rows 0..world-1: gathered triples; last row: result
+    bt = buf.to_torch()
+    rank = dist.get_rank() if world > 1 else 0
+    moments(x_local, out=buf[rank])
     if world > 1:
-        allv = torch.empty(world * 3, dtype=torch.float64, device=mm.device)
-        dist.all_gather_into_tensor(allv, loc)
-        allv = allv.reshape(world, 3)
-    else:
-        allv = loc.reshape(1, 3)
-    n, m, m2 = combine_moments([allv[k, 0] for k in range(world)], [allv[k, 1] for k in range(world)],
-                               [allv[k, 2] for k in range(world)])
-    return m2 / torch.clamp(n - ddof, min=0)
+        dist.all_gather_into_tensor(bt[:world].reshape(-1), bt[rank])
+    _lib.check(_lib.lib.b200_moments_merge(buf.ptr, world, float(ddof), buf[world].ptr, current_stream_ptr()))
+    return bt[world, 0]

@@ -81,10 +81,10 @@ extern "C" {
  * cupy/_core/_routines_statistics.pyx:611-655) */
 #define B200_OP_MEAN     8
 #define B200_OP_VAR      9    /* param = ddof; single pass Welford/Chan */
-#define B200_OP_MOMENTS  10   /* full reductions only: y = (mean, M2) in the accumulation float type (float for
-                                 fp16/fp32 inputs, double otherwise) -- what a caller needs to merge shards
-                                 (Chan) without a second pass; the reference has no counterpart (two passes,
-                                 cupy/_core/_routines_statistics.pyx:556-600) */
+#define B200_OP_MOMENTS  10   /* full reductions only: y = three doubles (n, mean, M2), accumulated in float for
+                                 fp16/fp32 inputs and double otherwise -- what a caller needs to merge shards
+                                 (Chan) without a second pass; out_dtype = float64.  The reference has no
+                                 counterpart (two passes, cupy/_core/_routines_statistics.pyx:556-600) */
 
 /* ---- status codes */
 #define B200_OK               0
@@ -191,6 +191,11 @@ int b200_reduce_workspace_bytes(const b200_reduce_desc_t* d, size_t* bytes);
 /* workspace must be zero-filled once when it is allocated; kernels leave it zeroed */
 int b200_reduce_run(const b200_reduce_desc_t* d, const void* x, void* y,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Sharded variance (the reference has no distributed var, cupyx/distributed/array/_array.py:744-747):
+ * Chan merge, in index order, of `count` (n, mean, M2) double triples as written by B200_OP_MOMENTS and
+ * all-gathered over the ranks.  out[0] = M2 / (n - ddof) (NaN when n - ddof <= 0), out[1] = mean, out[2] = n. */
+int b200_moments_merge(const double* triples, int count, double ddof, double* out, void* stream);
 
 /* ---- scan (inclusive, flat, decoupled look-back single pass) */
 int b200_scan_supported(int op, int in_dtype, int out_dtype);

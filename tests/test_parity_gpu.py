@@ -440,16 +440,34 @@ def test_scan_variants(cp):
 @pytest.mark.parametrize('dt', ['float32', 'float16', 'float64', 'int32', 'int64'])
 @pytest.mark.parametrize('n', [1, 7, 4096, 1 << 20, (1 << 22) + 3])
 def test_moments_single_pass_mean_m2(cp, n, dt):
-    """B200_OP_MOMENTS (what sharded_var exchanges): (mean, M2) of one pass vs float64 NumPy."""
+    """B200_OP_MOMENTS (what sharded_var exchanges): (n, mean, M2) of one pass vs float64 NumPy."""
     from cupy_b200._core._routines_statistics import moments
     a = rnd((n,), dt)
     got = moments(cp.asarray(a)).get()
-    want_dt = np.float32 if np.dtype(dt) in (np.dtype('float16'), np.dtype('float32')) else np.float64
-    assert got.dtype == want_dt and got.shape == (2,)
+    assert got.dtype == np.float64 and got.shape == (3,) and got[0] == n
     a64 = a.astype(np.float64)
-    tol = 1e-5 if want_dt == np.float32 else 1e-12
-    np.testing.assert_allclose(got[0], a64.mean(), rtol=tol, atol=tol * np.abs(a64).mean())
-    np.testing.assert_allclose(got[1], ((a64 - a64.mean()) ** 2).sum(), rtol=tol * 10, atol=1e-30)
+    tol = 1e-5 if np.dtype(dt) in (np.dtype('float16'), np.dtype('float32')) else 1e-12
+    np.testing.assert_allclose(got[1], a64.mean(), rtol=tol, atol=tol * np.abs(a64).mean())
+    np.testing.assert_allclose(got[2], ((a64 - a64.mean()) ** 2).sum(), rtol=tol * 10, atol=1e-30)
     # 2-D dense input is the same full reduction
     if n == 4096:
         np.testing.assert_allclose(moments(cp.asarray(a.reshape(64, 64))).get(), got, rtol=1e-6)
+
+
+def test_moments_merge_is_chan_in_rank_order(cp):
+    """b200_moments_merge against NumPy on the concatenated shards, empty shards included."""
+    import ctypes
+    from cupy_b200 import _lib
+    from cupy_b200._core._kernel import current_stream_ptr
+    from cupy_b200._core._routines_statistics import moments
+    shards = [rnd((k,), 'float64') for k in (1000, 1, 77777, 5)]
+    buf = cp.empty((len(shards) + 2, 3), np.float64)
+    for k, s in enumerate(shards):
+        moments(cp.asarray(s), out=buf[k])
+    buf[len(shards)] = cp.asarray(np.zeros(3))           # an empty shard: n = 0
+    for ddof in (0, 1):
+        _lib.check(_lib.lib.b200_moments_merge(buf.ptr, len(shards) + 1, float(ddof), buf[len(shards) + 1].ptr,
+                                               current_stream_ptr()))
+        got = buf[len(shards) + 1].get()
+        allx = np.concatenate(shards)
+        np.testing.assert_allclose(got, [allx.var(ddof=ddof), allx.mean(), allx.size], rtol=1e-12)
