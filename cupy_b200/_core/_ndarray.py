@@ -43,6 +43,25 @@ except Exception:  # pragma: no cover
     pass
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def _stream_ctx(stream):
+    """Context that makes `stream` (cupy_b200.cuda.Stream, torch stream or raw pointer) current."""
+    if stream is None:
+        return _NullCtx()
+    if hasattr(stream, '_st'):
+        return torch.cuda.stream(stream._st)
+    if isinstance(stream, torch.cuda.Stream):
+        return torch.cuda.stream(stream)
+    return torch.cuda.stream(torch.cuda.ExternalStream(int(getattr(stream, 'ptr', stream))))
+
+
 def current_stream_ptr():
     if _dryrun.enabled:
         return 0
@@ -424,29 +443,60 @@ class ndarray:
         raise ValueError('array does not own torch-visible memory')
 
     def get(self, stream=None, order='C', out=None, blocking=True):
-        """Device -> host copy (numpy.ndarray)."""
+        """Device -> host copy (cupy/_core/core.pyx `ndarray.get`): enqueued on `stream`
+        (default: the current stream).  With `out=` a page-locked C-contiguous array and
+        `blocking=False` the copy is asynchronous; otherwise the call returns when the data
+        is on the host."""
         a = self
         if not ((order == 'C' and a._c_contiguous) or (order == 'F' and a._f_contiguous)):
             a = a.copy(order=order if order in ('C', 'F') else 'C')
         if a.size == 0:
-            return numpy.empty(a._shape, a.dtype, order=order if order in ('C', 'F') else 'C')
-        host = a._bytes_view().cpu().numpy().view(a.dtype)
+            return numpy.empty(a._shape, a.dtype, order=order if order in ('C', 'F') else 'C') if out is None else out
+        ctx = _stream_ctx(stream)
+        with ctx:
+            if out is not None:
+                if not isinstance(out, numpy.ndarray):
+                    raise TypeError('Only numpy.ndarray can be obtained from cupy_b200.ndarray')
+                if out.dtype != a.dtype:
+                    raise TypeError('{} array cannot be obtained from {} array'.format(out.dtype, a.dtype))
+                if out.shape != a._shape:
+                    raise ValueError('Shape mismatch. Expected shape: {}, actual shape: {}'.format(a._shape, out.shape))
+                ok = out.flags.c_contiguous if order == 'C' else out.flags.f_contiguous
+                if not ok:
+                    raise RuntimeError('`out` cannot be specified when copying to non-contiguous ndarray')
+                flat = out.reshape(-1, order='C' if order == 'C' else 'F') if out.ndim > 1 else out
+                dst = torch.from_numpy(flat.view(numpy.uint8) if flat.ndim == 1 else flat.reshape(-1).view(numpy.uint8))
+                dst.copy_(a._bytes_view(), non_blocking=not blocking)
+                if blocking:
+                    torch.cuda.current_stream().synchronize()
+                return out
+            host = a._bytes_view().cpu().numpy().view(a.dtype)
         if order == 'F' and a.ndim > 1:
             host = host.reshape(a._shape[::-1]).T
         else:
             host = host.reshape(a._shape)
-        if out is not None:
-            out[...] = host
-            return out
         return host
 
     def set(self, arr, stream=None):
-        arr = numpy.ascontiguousarray(arr, dtype=self.dtype)
+        """Host -> device copy (cupy/_core/core.pyx `ndarray.set`), enqueued on `stream`
+        (default: the current stream); asynchronous when `arr` is page-locked and laid out
+        like this array."""
+        if not isinstance(arr, numpy.ndarray):
+            raise TypeError('Only numpy.ndarray can be set to cupy_b200.ndarray')
+        if arr.dtype != self.dtype:
+            raise TypeError('{} array cannot be set to {} array'.format(arr.dtype, self.dtype))
         if arr.shape != self._shape:
             raise ValueError('Shape mismatch. Old shape: %s, new shape: %s' % (self._shape, arr.shape))
-        tmp = asarray(arr)
-        from cupy_b200._core import _kernel
-        _kernel.elementwise_copy(tmp, self)
+        with _stream_ctx(stream):
+            if self._c_contiguous and arr.flags.c_contiguous and self.size:
+                src = torch.from_numpy(arr.reshape(-1).view(numpy.uint8))
+                self._bytes_view().copy_(src, non_blocking=True)
+                return
+            if self.size == 0:
+                return
+            tmp = asarray(arr)
+            from cupy_b200._core import _kernel
+            _kernel.elementwise_copy(tmp, self)
 
     def item(self):
         return self.get().item()

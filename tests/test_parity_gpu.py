@@ -471,3 +471,37 @@ def test_moments_merge_is_chan_in_rank_order(cp):
         got = buf[len(shards) + 1].get()
         allx = np.concatenate(shards)
         np.testing.assert_allclose(got, [allx.var(ddof=ddof), allx.mean(), allx.size], rtol=1e-12)
+
+
+def test_streams_events_and_async_get_set(cp):
+    """cupy_b200.cuda.Stream / Event and ndarray.set / get(stream=, out=, blocking=) -- the
+    reference's cupy.cuda.Stream surface (cupy/cuda/stream.pyx:101-520) around the hot path."""
+    n = 1 << 20
+    hx = cp.cuda.empty_pinned((n,), np.float32)
+    hz = cp.cuda.empty_pinned((n,), np.float32)
+    hx[:] = np.arange(n, dtype=np.float32)
+    s1, s2 = cp.cuda.Stream(non_blocking=True), cp.cuda.Stream(non_blocking=True)
+    dx = cp.empty((n,), np.float32)
+    dx.set(hx, stream=s1)
+    ev = s1.record()
+    s2.wait_event(ev)
+    with s2:
+        assert cp.cuda.get_current_stream() == s2
+        dz = dx * 2 + 1
+        dz.get(out=hz, blocking=False)
+    s2.synchronize()
+    assert s2.done
+    np.testing.assert_array_equal(hz, hx * 2 + 1)
+    e0, e1 = cp.cuda.Event(), cp.cuda.Event()
+    e0.record()
+    (dx + dx).sum()
+    e1.record()
+    e1.synchronize()
+    assert cp.cuda.get_elapsed_time(e0, e1) >= 0
+    with pytest.raises(TypeError):
+        dx.set(hx.astype(np.float64))
+    with pytest.raises(ValueError):
+        dx.set(hx[:5])
+    with pytest.raises(TypeError):
+        dx.get(out=np.empty(n, np.float64))
+    np.testing.assert_array_equal(dx.reshape(1024, 1024).get(out=np.empty((1024, 1024), np.float32)), hx.reshape(1024, 1024))
