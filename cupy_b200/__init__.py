@@ -22,6 +22,7 @@ from cupy_b200._core._routines_statistics import (  # noqa: F401
     amax, amin, argmax, argmin, mean, var, std)
 
 from cupy_b200 import cuda  # noqa: F401,E402
+from cupy_b200._core.fusion import fuse  # noqa: F401,E402
 
 abs = absolute
 max = amax

@@ -31,8 +31,9 @@ class EwSpec:
     per-call layout (variant / vector width / dims)."""
 
     def __init__(self, mode, operation, preamble='', loop_prep='', after_loop='', options=(),
-                 in_types=None, out_types=None, has_where=False, type_map=()):
-        self.mode = mode                  # 'elementwise' (user kernel) | 'ufunc'
+                 in_types=None, out_types=None, has_where=False, type_map=(), write_only_outputs=False):
+        self.mode = mode
+        self.write_only_outputs = write_only_outputs   # generated text (cupy_b200.fuse): outputs are only assigned                  # 'elementwise' (user kernel) | 'ufunc'
         self.operation = operation
         self.preamble = preamble
         self.loop_prep = loop_prep
@@ -52,7 +53,8 @@ class EwSpec:
         s = self._bound.get(type_map)
         if s is None:
             s = EwSpec(self.mode, self.operation, self.preamble, self.loop_prep, self.after_loop,
-                       self.options, self.in_types, self.out_types, self.has_where, type_map)
+                       self.options, self.in_types, self.out_types, self.has_where, type_map,
+                       self.write_only_outputs)
             self._bound[type_map] = s
         return s
 
@@ -162,7 +164,7 @@ def render_elementwise(spec, name, args, params, variant, vec, unroll, threads, 
             else:
                 # user kernel: outputs are read-modify-write capable unless the operation
                 # provably writes them first
-                if not (is_out and writes_first(spec.operation, p.name)):
+                if not (is_out and (spec.write_only_outputs or writes_first(spec.operation, p.name))):
                     loads.append('    _t.template load<_FULL>(%d, %s);' % (k, reg))
                 if is_out:
                     binds.append('        %s& %s = %s[_u][_k];' % (p.ctype, p.name, reg))

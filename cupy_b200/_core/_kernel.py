@@ -430,6 +430,7 @@ class ElementwiseKernel:
         self.preamble = preamble
         self.no_return = no_return
         self.return_tuple = return_tuple
+        write_only = bool(kwargs.pop('_write_only_outputs', False))     # private: text generated by cupy_b200.fuse
         self.kwargs = kwargs
         bad = set(kwargs) - {'options', 'loop_prep', 'after_loop'}
         if bad:
@@ -442,7 +443,7 @@ class ElementwiseKernel:
         self._spec = _codegen.EwSpec(
             mode='elementwise', operation=operation, preamble=preamble,
             loop_prep=kwargs.get('loop_prep', ''), after_loop=kwargs.get('after_loop', ''),
-            options=tuple(kwargs.get('options', ())))
+            options=tuple(kwargs.get('options', ())), write_only_outputs=write_only)
 
     def __call__(self, *args, **kwargs):
         size = kwargs.pop('size', -1)

@@ -195,7 +195,7 @@ def prod(a, axis=None, dtype=None, out=None, keepdims=False):
 
 
 def _as_array(a):
-    if isinstance(a, ndarray):
+    if isinstance(a, ndarray) or hasattr(a, '__cupy_override_reduction_kernel__'):   # arrays, fusion variables
         return a
     from cupy_b200._core import _ndarray
     return _ndarray.asarray(a)

@@ -94,6 +94,16 @@ def main():
         fused = cp.ElementwiseKernel('T x, T v', 'T z', 'z = exp(x) + v', 'expadd')
         report('fused exp(x^T)+v ElementwiseKernel', 8 * nel, lambda: fused(xt, v, out), iters=10)
         report('copy transposed (ascontiguous)', 8 * nel, lambda: cp.elementwise_copy(xt, out), iters=10)
+        ff = cp.fuse(kernel_name='fuse_expadd')(lambda x, v: cp.exp(x) + v)
+        report('cupy_b200.fuse: exp(x^T)+v', 8 * nel, lambda: ff(xt, v), iters=10)
+        fr = cp.fuse(kernel_name='fuse_sqsum')(lambda x, y: cp.sum((x - y) * (x - y), axis=2))
+        report('cupy_b200.fuse: sum((x-tmp)^2, axis=2) contiguous', 8 * nel, lambda: fr(out, tmp), iters=10)
+        f1 = cp.fuse(kernel_name='fuse_sumsq')(lambda x: cp.sum(x * x))
+        report('cupy_b200.fuse: sum(x*x) one input, full', 4 * nel, lambda: f1(out), iters=10)
+        f2 = cp.fuse(kernel_name='fuse_sumsq_ax')(lambda x: cp.sum(x * x, axis=2))
+        report('cupy_b200.fuse: sum(x*x, axis=2) one input, rows', 4 * nel, lambda: f2(out), iters=10)
+        fa = cp.fuse(kernel_name='fuse_x2p1')(lambda x: x * 2 + 1)
+        report('cupy_b200.fuse: x*2+1 (config 1 chain, 2^28)', 8 * nel, lambda: fa(out), iters=10)
         k1 = cp.ElementwiseKernel('T x', 'T z', 'z = exp(x)', 'jit_exp')
         k2 = cp.ElementwiseKernel('T x, T v', 'T z', 'z = x + v', 'jit_addv')
         k3 = cp.ElementwiseKernel('T x, T v', 'T z', 'z = __expf(x) + v', 'jit_fastexp_addv')
