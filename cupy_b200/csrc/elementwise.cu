@@ -7,6 +7,7 @@
 // Replaces cupy/_core/_kernel.pyx:1024-1100 (_get_ufunc_kernel: JIT per dtype /
 // ndim / contiguity) + cupy/cuda/function.pyx:153-171 (linear_launch, 128-thread
 // blocks, one element per thread).
+#include <algorithm>
 #include "common.h"
 #include "elementwise_registry.h"
 
@@ -85,6 +86,7 @@ extern "C" __attribute__((visibility("default"))) int b200_ufunc_launch(int ufun
             if (plan->vec >= k->vec && k->vec > 1) { fn = plan->idx32 ? k->row_v32 : k->row_v64; eff.vec = k->vec; }
             else { fn = plan->idx32 ? k->row_132 : k->row_164; eff.vec = 1; }
             unroll = k->unroll_row;
+            p.fdiv_chunks = FastDiv(uint32_t(std::min<int64_t>(plan->shape[plan->ndim - 1] / eff.vec, 0xfffffffe)));
             break;
         case B200_EW_TILED:
             fn = k->tiled;

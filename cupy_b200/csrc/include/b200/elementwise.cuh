@@ -42,6 +42,7 @@ struct EwParams {
     int64_t  shape[kMaxNdim];
     int64_t  cstride[kMaxNdim];    // C-order element strides of `shape` (for the linear index `i`)
     FastDiv  fdiv[kMaxNdim];       // fast division by shape[d] (valid when size < 2^31)
+    FastDiv  fdiv_chunks;          // ROWWISE: fast division by shape[ndim-1] / vec (vectors per row)
     EwArg    arg[kMaxArgs];
 };
 
@@ -140,12 +141,16 @@ struct FlatTiler {
 // Host guarantees for VEC > 1: shape[ndim-1] % VEC == 0 and VEC*sizeof(T)
 // alignment of every unit-stride operand (base and outer strides).
 // ---------------------------------------------------------------------------
+template <bool IDX32> struct row_offset { typedef int64_t type; };
+template <> struct row_offset<true> { typedef int32_t type; };      // the planner guarantees every span < 2^31
+
 template <int NARGS, int VEC, int UNROLL, int THREADS, bool IDX32>
 struct RowTiler {
     static constexpr int kV = VEC, kU = UNROLL;
+    typedef typename row_offset<IDX32>::type off_t;
     const EwParams& p;
     int64_t inner, chunks, total, wbase;
-    int64_t off[UNROLL][NARGS];
+    off_t off[UNROLL][NARGS];
     int64_t lin[UNROLL];
     bool ok[UNROLL];
 
@@ -166,25 +171,24 @@ struct RowTiler {
             lin[u] = 0;
             if (!ok[u]) continue;
             if (IDX32) {
-                uint32_t rest = static_cast<uint32_t>(w), c;
-                // innermost: chunk index
-                {
-                    uint32_t q = rest / static_cast<uint32_t>(chunks);
-                    c = rest - q * static_cast<uint32_t>(chunks);
-                    rest = q;
-                }
-                const int64_t e0 = int64_t(c) * VEC;
+                // all 32-bit: one multiply-high division per dim, 32-bit offsets per operand
+                uint32_t rest = static_cast<uint32_t>(w), c, q;
+                p.fdiv_chunks.divmod(rest, q, c);     // innermost: chunk index
+                rest = q;
+                const uint32_t e0 = c * VEC;
                 lin[u] = e0;
 #pragma unroll
-                for (int a = 0; a < NARGS; ++a) off[u][a] = e0 * p.arg[a].strides[p.ndim - 1];
+                for (int a = 0; a < NARGS; ++a)
+                    off[u][a] = static_cast<off_t>(e0 * static_cast<uint32_t>(p.arg[a].strides[p.ndim - 1]));
 #pragma unroll 1
                 for (int d = p.ndim - 2; d >= 0; --d) {
-                    uint32_t q, r;
+                    uint32_t r;
                     p.fdiv[d].divmod(rest, q, r);
                     rest = q;
                     lin[u] += int64_t(r) * p.cstride[d];
 #pragma unroll
-                    for (int a = 0; a < NARGS; ++a) off[u][a] += int64_t(r) * p.arg[a].strides[d];
+                    for (int a = 0; a < NARGS; ++a)
+                        off[u][a] += static_cast<off_t>(r * static_cast<uint32_t>(p.arg[a].strides[d]));
                 }
             } else {
                 int64_t rest = w;

@@ -197,21 +197,44 @@ template <> B200_DEVICE int ext_to_cmp<bool>(const bool& v) { return v ? 1 : 0; 
 // against itself: a lane that was never updated reports its first index.  NaN never wins a
 // strict comparison either, so it is detected per batch with a NaN-propagating max
 // (FMNMX3.NAN) and located out of line -- first NaN of each lane.
+template <class T> struct is_f16 { static constexpr bool value = false; };
+template <> struct is_f16<float16> { static constexpr bool value = true; };
+
 template <class In, class Index, bool kMax, int U, int V>
 struct ArgLanes {
     typedef ArgOp<In, Index, kMax> Op;
     typedef typename Op::acc_t acc_t;
     typedef typename ext_type<In>::type E;
     static constexpr bool kFloat = is_floating<In>::value;
+    // float16: the running values live in half2 pairs, so a pair costs ONE packed compare
+    // (HSETP2, two predicates), ONE packed max (HMNMX2) and two index selects -- 2 instructions
+    // per element instead of ~4 (scalar selects of 16-bit values need PRMT packing).  max(val, e)
+    // equals "e > val ? e : val" here because val is never NaN and a NaN e loses both ways.
+    static constexpr bool kPacked = is_f16<In>::value && (V % 2 == 0);
+    static constexpr int kPairs = kPacked ? V / 2 : 1;
     const Op& op;
-    E val[V];
+    E val[kPacked ? 1 : V];
+    __half2 val2[kPairs];
     Index jst[V];        // index (without the lane offset k*ks) of the element that set val; -1 = never updated
     Index nan_j[V];      // first NaN of the lane (full index); -1 = none
     Index j_first, ks_;  // first index this thread saw (lane 0, without k*ks); -1 = saw nothing
 
+    B200_DEVICE E get_val(int k) const {
+        if constexpr (kPacked) return (k & 1) ? __high2half(val2[k >> 1]) : __low2half(val2[k >> 1]);
+        else return val[k];
+    }
+    B200_DEVICE void set_val(int k, const E& e) {
+        if constexpr (kPacked) {
+            if (k & 1) val2[k >> 1] = __halves2half2(__low2half(val2[k >> 1]), e);
+            else val2[k >> 1] = __halves2half2(e, __high2half(val2[k >> 1]));
+        } else {
+            val[k] = e;
+        }
+    }
+
     B200_DEVICE explicit ArgLanes(const Op& op_) : op(op_), j_first(-1), ks_(0) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) { val[k] = ext_identity<E, kMax>::get(); jst[k] = -1; nan_j[k] = -1; }
+        for (int k = 0; k < V; ++k) { set_val(k, ext_identity<E, kMax>::get()); jst[k] = -1; nan_j[k] = -1; }
     }
     B200_DEVICE void fold(const Pack<In, V> (&v)[U], Index j0, Index us, Index ks) {
         ks_ = ks;
@@ -219,12 +242,24 @@ struct ArgLanes {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const Index ju = j0 + u * us;
+            if constexpr (kPacked) {
 #pragma unroll
-            for (int k = 0; k < V; ++k) {
-                const E e = to_ext(v[u][k]);
-                const bool p = ext_better<kMax>(e, val[k]);
-                val[k] = p ? e : val[k];
-                jst[k] = p ? ju : jst[k];
+                for (int q = 0; q < kPairs; ++q) {
+                    const __half2 e2 = __halves2half2(to_ext(v[u][2 * q]), to_ext(v[u][2 * q + 1]));
+                    const bool p0 = ext_better<kMax>(__low2half(e2), __low2half(val2[q]));
+                    const bool p1 = ext_better<kMax>(__high2half(e2), __high2half(val2[q]));
+                    val2[q] = kMax ? __hmax2(val2[q], e2) : __hmin2(val2[q], e2);
+                    jst[2 * q] = p0 ? ju : jst[2 * q];
+                    jst[2 * q + 1] = p1 ? ju : jst[2 * q + 1];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const E e = to_ext(v[u][k]);
+                    const bool p = ext_better<kMax>(e, val[k]);
+                    val[k] = p ? e : val[k];
+                    jst[k] = p ? ju : jst[k];
+                }
             }
         }
         if (kFloat) {
@@ -251,8 +286,8 @@ struct ArgLanes {
     B200_DEVICE void fold_one_lane(int k, const In& x, Index j) {
         const E e = to_ext(x);
         if (k == 0) j_first = j_first < 0 ? j : j_first;
-        const bool p = ext_better<kMax>(e, val[k]);
-        val[k] = p ? e : val[k];
+        const bool p = ext_better<kMax>(e, get_val(k));
+        if (p) set_val(k, e);
         jst[k] = p ? (j - k * ks_) : jst[k];
         if (kFloat && ext_is_nan(e) && nan_j[k] < 0) nan_j[k] = j;
     }
@@ -264,7 +299,7 @@ struct ArgLanes {
         // start-value candidate too; it can only tie with real start-value elements, and the
         // lowest index among those is always a real one.)
         if (j_first >= 0) {
-            r.value = ext_to_cmp<In>(val[k]);
+            r.value = ext_to_cmp<In>(get_val(k));
             r.index = (jst[k] >= 0 ? jst[k] : j_first) + k * ks_;
         }
         if (kFloat && nan_j[k] >= 0) {
@@ -358,6 +393,17 @@ struct MomentsOp {
 // whatever U is -- so U can follow the memory system (bytes in flight), not the register file.
 // The very first batch is centred on its own first element.
 // ---------------------------------------------------------------------------
+// x - c in the accumulation type.  float16 input with a float accumulator uses the sm_100a
+// mixed-precision subtract (sub.f32.f16 -> FHADD): the half -> float conversion is free.
+template <class In, class F>
+B200_DEVICE F centred(const In& x, const F& c) { return static_cast<F>(x) - c; }
+template <>
+B200_DEVICE float centred<float16, float>(const float16& x, const float& c) {
+    float d;
+    asm("sub.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(__half_as_ushort(x.raw())), "f"(c));
+    return d;
+}
+
 template <class In, class F, class Out, int kMode, int U, int V>
 struct MomentLanes {
     typedef MomentsOp<In, F, Out, kMode> Op;
@@ -383,7 +429,7 @@ struct MomentLanes {
             F s1 = F(0), s2 = F(0);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const F d = static_cast<F>(v[u][k]) - c;
+                const F d = centred<In, F>(v[u][k], c);
                 s1 += d;
                 s2 += d * d;
             }

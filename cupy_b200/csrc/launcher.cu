@@ -76,6 +76,10 @@ int fill_ew_params(const b200_ew_plan_t* plan, int nargs, const b200_operand_t* 
         const uint64_t s = uint64_t(plan->shape[d]);
         p.fdiv[d] = FastDiv(s < 0xffffffffull ? uint32_t(s) : 1u);
     }
+    {
+        const uint64_t chunks = uint64_t(plan->shape[plan->ndim - 1]) / uint64_t(std::max(1, plan->vec));
+        p.fdiv_chunks = FastDiv(chunks && chunks < 0xffffffffull ? uint32_t(chunks) : 1u);
+    }
     for (int a = 0; a < nargs; ++a) {
         if (args[a].kind == B200_KIND_SCALAR) {
             p.scalar_mask |= 1u << a;
@@ -180,7 +184,8 @@ unsigned ew_grid(const b200_ew_plan_t* plan, int threads, int unroll, int sm_cou
     blocks = (work + per_block - 1) / per_block;
     // persistent: enough resident blocks to cover HBM latency, then grid-stride.
     // plan->reserved bits 8..23: blocks per SM override (tuning sweeps)
-    const int per_sm = ((plan->reserved >> 8) & 0xffff) ? int((plan->reserved >> 8) & 0xffff) : (2048 / threads) * 4;
+    const int per_sm = ((plan->reserved >> 8) & 0xffff) ? int((plan->reserved >> 8) & 0xffff)
+                       : (2048 / threads) * (plan->variant == B200_EW_ROWWISE ? 8 : 4);
     const int64_t cap = int64_t(sm_count) * per_sm;
     return unsigned(std::max<int64_t>(1, std::min(blocks, cap)));
 }
