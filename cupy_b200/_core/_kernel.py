@@ -321,7 +321,7 @@ def _prod(shape):
 tunables = {
     'threads': 256,
     'flat_unroll': 4,
-    'row_unroll': 1,
+    'row_unroll': 2,
     'blocks_per_sm': 0,       # 0 = library default
     'tma_stages': 0,          # TILED_TMA ring depth, 0 = library default
     'reg_unroll': 0,          # TILED_REG blocks per thread, 0 = library default (8 vector loads in flight)

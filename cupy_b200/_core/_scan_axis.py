@@ -1,48 +1,64 @@
-"""cumsum / cumprod along one axis ("next").
+"""cumsum / cumprod along one axis.
 
-Reference: `_proc_as_batch` + `_batch_scan_op` (cupy/_core/_routines_math.pyx:
-499-699): roll the axis to the end, reshape to (lines, n), scan every line.
-Round-1 implementation: correct and simple -- the lines are made contiguous and
-each line is scanned serially by one thread through a `raw` ElementwiseKernel.
-The flat look-back scan (the measured config) does not come through here.
+Reference: `_proc_as_batch` + `_batch_scan_op` (cupy/_core/_routines_math.pyx:499-699):
+roll the axis to the end (transposing copy), run log2(n) doubling passes over the whole
+array, roll back (another copy).  Here a dense array is viewed in place as
+x[outer][n][inner] and `b200_scan_axis_run` scans n in ONE pass (read once, write once),
+converting the input dtype on load (csrc/scan_axis.cu).  Only non-dense inputs / outputs are
+staged through a C-contiguous copy first.
 """
 from __future__ import annotations
 
+import ctypes
+
 from cupy_b200 import _lib
-from cupy_b200._core import _kernel
+from cupy_b200._core import _dryrun, _kernel, _scalar
+from cupy_b200._core._kernel import current_stream_ptr
 from cupy_b200._core._ndarray import ndarray
 
-_memo = {}
 
-
-def _line_kernel(op):
-    k = _memo.get(op)
-    if k is None:
-        sym = '+' if op == _lib.OP_CUMSUM else '*'
-        k = _kernel.ElementwiseKernel(
-            'int64 n', 'raw T y',
-            'T acc = y[i * n]; for (long long j = 1; j < n; ++j) { acc = acc %s y[i * n + j]; y[i * n + j] = acc; }' % sym,
-            'cupy_scan_lines_' + ('sum' if op == _lib.OP_CUMSUM else 'prod'))
-        _memo[op] = k
-    return k
+def _prod(t):
+    r = 1
+    for s in t:
+        r *= int(s)
+    return r
 
 
 def scan_axis(a, axis, op, dtype, out):
-    nd = a.ndim
-    if a.shape[axis] == 0 or a.size == 0:
-        res = ndarray(a.shape, dtype)
+    if out is not None and out.shape != a.shape:
+        raise ValueError('Provided out is the wrong size for the reduction')
+    in_id, out_id = _scalar.dtype_id(a.dtype), _scalar.dtype_id(dtype)
+    if a.size == 0:
+        return out if out is not None else ndarray(a.shape, dtype)
+    src = a
+    if not _lib.lib.b200_scan_supported(op, in_id, out_id):
+        # dtype pair without a prebuilt kernel: convert first (one extra pass), then scan in the out dtype
+        src = ndarray(a.shape, dtype)
+        _kernel.elementwise_copy(a, src)
+        in_id = out_id
+        if not _lib.lib.b200_scan_supported(op, in_id, out_id):
+            raise NotImplementedError('scan of dtype %s is outside the prebuilt table' % (dtype,))
+    if not src._c_contiguous:
+        c = ndarray(src.shape, src.dtype)
+        _kernel.elementwise_copy(src, c)
+        src = c
+    direct = out is not None and out._c_contiguous and out.dtype == dtype
+    dst = out if direct else ndarray(a.shape, dtype)
+    outer, n, inner = _prod(a.shape[:axis]), int(a.shape[axis]), _prod(a.shape[axis + 1:])
+    if _dryrun.enabled:
+        _dryrun.record('prebuilt_scan_axis', op=op, outer=outer, n=n, inner=inner)
     else:
-        perm = [i for i in range(nd) if i != axis] + [axis]
-        t = a.transpose(perm)
-        lines = ndarray(t.shape, dtype)            # C-contiguous, scanned axis innermost
-        _kernel.elementwise_copy(t, lines)
-        n = a.shape[axis]
-        _line_kernel(op)(n, lines, size=lines.size // n)
-        inv = [perm.index(i) for i in range(nd)]
-        res = lines.transpose(inv)
-    if out is not None:
-        if out.shape != a.shape:
-            raise ValueError('Provided out is the wrong size for the reduction')
-        _kernel.elementwise_copy(res, out)
+        st = current_stream_ptr()
+        need = ctypes.c_size_t()
+        _lib.check(_lib.lib.b200_scan_axis_workspace_bytes(outer, n, inner, ctypes.byref(need)))
+        ws_ptr, ws_bytes = (0, 0)
+        if need.value:
+            # segment totals: plain scratch (no ticket protocol), so not the zero-kept reduction workspace
+            scratch = ndarray((need.value,), 'uint8')
+            ws_ptr, ws_bytes = scratch.ptr, need.value
+        _lib.check(_lib.lib.b200_scan_axis_run(op, in_id, out_id, src.ptr, dst.ptr, outer, n, inner,
+                                               ws_ptr, ws_bytes, st))
+    if out is not None and not direct:
+        _kernel.elementwise_copy(dst, out)
         return out
-    return res.copy() if not res._c_contiguous else res
+    return dst

@@ -112,6 +112,9 @@ _EXPORTS = {
     'b200_scan_supported': (c_int, [c_int, c_int, c_int]),
     'b200_scan_workspace_bytes': (c_int, [c_int64, c_int, POINTER(c_size_t)]),
     'b200_scan_run': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
+    'b200_scan_axis_workspace_bytes': (c_int, [c_int64, c_int64, c_int64, POINTER(c_size_t)]),
+    'b200_scan_axis_run': (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_size_t,
+                                   c_void_p]),
     'b200_jit_compile': (c_int, [c_char_p, c_char_p, c_int, POINTER(c_char_p), POINTER(c_void_p), POINTER(c_size_t)]),
     'b200_jit_last_log': (c_char_p, []),
     'b200_jit_free_image': (None, [c_void_p]),

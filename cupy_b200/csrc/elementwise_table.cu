@@ -110,7 +110,7 @@ static EwKernels make_kernels() {
     constexpr int N = F::nin + 1;
     constexpr int maxsz = max_size2<typename F::out_t>(int(sizeof(typename F::in0_t)));
     constexpr int V = (16 / maxsz) < 1 ? 1 : (16 / maxsz);
-    constexpr int UF = 4, UR = 1;   // ROWWISE: occupancy beats unrolling (per-unroll offsets cost registers): B200 sweep, profiles/r01_row_probe.log
+    constexpr int UF = 4, UR = 2;   // ROWWISE: B200 sweep in profiles/r01_row_probe.log (2 beats 1 and 4 once the index math is 32-bit)
     EwKernels k;
     k.flat_v = reinterpret_cast<const void*>(&ew_kernel<FlatTiler<N, V, UF, kEwThreads>, F>);
     k.flat_1 = reinterpret_cast<const void*>(&ew_kernel<FlatTiler<N, 1, UF, kEwThreads>, F>);

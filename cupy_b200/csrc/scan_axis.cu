@@ -1,0 +1,255 @@
+// scan_axis.cu -- cumsum / cumprod along ONE axis of a dense array viewed as
+// x[outer][n][inner] (C order), scanning n.  No transposes, no `astype` pre-pass: the input
+// dtype is converted on load and the result is written in place of the output layout.
+//
+// Replaces `_proc_as_batch` + `_batch_scan_op` (cupy/_core/_routines_math.pyx:499-699), which
+// rolls the axis to the end (a transposing copy each way) and runs a log-step Hillis-Steele
+// kernel per doubling stride over the whole array (log2(n) passes over HBM).  Here it is one
+// pass: read once, write once.
+//
+//   inner == 1 (scan along the contiguous axis): LINES kernels.  A line is walked in tiles of
+//       GROUP x ITEMS consecutive elements by a GROUP of threads (a block for long lines, a
+//       warp for short ones): 16-byte loads, thread-serial scan of its ITEMS, shuffle scan
+//       across the warp, shared-memory scan across the warps, running carry in a register.
+//   inner > 1 (scan along a strided axis): COLS kernel.  A thread owns V adjacent columns and
+//       walks down n with U rows of loads in flight; a warp instruction reads 32*V adjacent
+//       elements of one row, so every access is a full line; the running sums stay in registers.
+#include <algorithm>
+
+#include "common.h"
+#include "include/b200/scan.cuh"
+#include "scan_table.h"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------
+template <class In, class Acc, class Out, class Op, int GROUP, int ITEMS>
+__global__ void __launch_bounds__(256) scan_lines_kernel(const In* __restrict__ x, Out* __restrict__ y, int64_t lines,
+                                                         int64_t n, int in_vec, int out_vec) {
+    constexpr int THREADS = 256;
+    constexpr int GROUPS = THREADS / GROUP;
+    constexpr int GWARPS = GROUP / 32;
+    __shared__ Acc warp_tot[THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = tid / GROUP, gt = tid % GROUP, gw = gt >> 5;
+    const int64_t rounds = (lines + int64_t(gridDim.x) * GROUPS - 1) / (int64_t(gridDim.x) * GROUPS);
+    for (int64_t r = 0; r < rounds; ++r) {
+        const int64_t line = (r * gridDim.x + blockIdx.x) * GROUPS + g;
+        const bool live = line < lines;                 // dead groups still reach the barriers
+        const In* xl = x + (live ? line : 0) * n;
+        Out* yl = y + (live ? line : 0) * n;
+        Acc carry = Op::template identity<Acc>();
+        for (int64_t base = 0; base < n; base += int64_t(GROUP) * ITEMS) {
+            const int64_t i0 = base + int64_t(gt) * ITEMS;
+            Acc item[ITEMS];
+            if (live && in_vec && i0 + ITEMS <= n) {
+                Pack<In, ITEMS> v;
+                load_pack(v, xl + i0);
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j) item[j] = static_cast<Acc>(v[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j)
+                    item[j] = (live && i0 + j < n) ? static_cast<Acc>(xl[i0 + j]) : Op::template identity<Acc>();
+            }
+#pragma unroll
+            for (int j = 1; j < ITEMS; ++j) item[j] = Op::combine(item[j - 1], item[j]);
+            Acc incl = item[ITEMS - 1];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                Acc t = shfl_up_any(incl, d);
+                if (lane >= d) incl = Op::combine(t, incl);
+            }
+            Acc excl = shfl_up_any(incl, 1);
+            if (lane == 0) excl = Op::template identity<Acc>();
+            Acc tile_tot = shfl_any(incl, 31);
+            if (GWARPS > 1) {
+                if (lane == 31) warp_tot[warp] = incl;
+                __syncthreads();
+                Acc before = Op::template identity<Acc>();
+                tile_tot = Op::template identity<Acc>();
+#pragma unroll
+                for (int w = 0; w < GWARPS; ++w) {
+                    const Acc t = warp_tot[g * GWARPS + w];
+                    if (w < gw) before = Op::combine(before, t);
+                    tile_tot = Op::combine(tile_tot, t);
+                }
+                excl = Op::combine(before, excl);
+                __syncthreads();
+            }
+            const Acc pre = Op::combine(carry, excl);
+            if (live && out_vec && i0 + ITEMS <= n) {
+                Pack<Out, ITEMS> o;
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j) o[j] = static_cast<Out>(Op::combine(pre, item[j]));
+                store_pack(yl + i0, o);
+            } else if (live) {
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j)
+                    if (i0 + j < n) yl[i0 + j] = static_cast<Out>(Op::combine(pre, item[j]));
+            }
+            carry = Op::combine(carry, tile_tot);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// MODE 0: plain scan.  When outer * inner / V threads cannot fill the GPU, n is cut into S
+// segments of `seg` rows that are scanned independently: MODE 1 = segment totals only
+// (tot[o][s][inner], no output), then the totals are scanned along s in place (MODE 0 on
+// tot), then MODE 2 = scan of every segment starting from the inclusive total of the
+// segments before it.  That reads x twice (12 instead of 8 bytes per float32 element) but keeps
+// every SM busy; a column-parallel single pass over 4096 columns runs at 10 % of peak.
+template <class In, class Acc, class Out, class Op, int V, int U, int MODE>
+__global__ void __launch_bounds__(256) scan_cols_kernel(const In* __restrict__ x, Out* __restrict__ y, int64_t outer,
+                                                        int64_t n, int64_t inner, int64_t S, int64_t seg,
+                                                        Acc* __restrict__ tot) {
+    const int64_t chunks = inner / V;
+    const int64_t total = outer * S * chunks;
+    for (int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; c < total; c += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t ic = c % chunks, os = c / chunks;
+        const int64_t sg = os % S, o = os / S;
+        const int64_t j0 = sg * seg, j1 = (j0 + seg < n) ? j0 + seg : n;
+        const In* xp = x + o * n * inner + ic * V;
+        Out* yp = y + o * n * inner + ic * V;
+        Acc acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = Op::template identity<Acc>();
+        if (MODE == 2 && sg > 0) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = tot[((o * S + sg - 1) * inner) + ic * V + k];
+        }
+        int64_t j = j0;
+        for (; j + U <= j1; j += U) {
+            Pack<In, V> v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) load_pack(v[u], xp + (j + u) * inner);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                Pack<Out, V> w;
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    acc[k] = Op::combine(acc[k], static_cast<Acc>(v[u][k]));
+                    w[k] = static_cast<Out>(acc[k]);
+                }
+                if (MODE != 1) store_pack(yp + (j + u) * inner, w);
+            }
+        }
+        for (; j < j1; ++j) {
+            Pack<In, V> v;
+            load_pack(v, xp + j * inner);
+            Pack<Out, V> w;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                acc[k] = Op::combine(acc[k], static_cast<Acc>(v[k]));
+                w[k] = static_cast<Out>(acc[k]);
+            }
+            if (MODE != 1) store_pack(yp + j * inner, w);
+        }
+        if (MODE == 1) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) tot[(o * S + sg) * inner + ic * V + k] = acc[k];
+        }
+    }
+}
+
+// segments to cut n into so that outer * S * inner / V threads fill the GPU (1 = no split)
+static int64_t axis_split(int64_t outer, int64_t n, int64_t inner, int sm_count) {
+    if (inner <= 1) return 1;
+    const int64_t cols = outer * inner;            // upper bound on threads (V = 1)
+    const int64_t target = int64_t(sm_count) * 2048;
+    if (cols * 4 >= target * 4 / 2 || n < 256) return 1;
+    int64_t S = (target + cols - 1) / cols;
+    S = std::min<int64_t>(S, n / 64);
+    return std::max<int64_t>(S, 1);
+}
+
+template <class In, class Out> constexpr int axis_vec() {
+    return (16 / int(sizeof(In) > sizeof(Out) ? sizeof(In) : sizeof(Out))) < 1
+               ? 1 : (16 / int(sizeof(In) > sizeof(Out) ? sizeof(In) : sizeof(Out)));
+}
+
+template <class In, class Acc, class Out, class Op>
+static int run_axis(const void* xv, void* yv, int64_t outer, int64_t n, int64_t inner, void* ws, size_t ws_bytes,
+                    int sm_count, cudaStream_t s) {
+    const In* x = static_cast<const In*>(xv);
+    Out* y = static_cast<Out*>(yv);
+    const uintptr_t xa = reinterpret_cast<uintptr_t>(xv), ya = reinterpret_cast<uintptr_t>(yv);
+    if (inner == 1) {
+        constexpr int ITEMS = (16 / int(sizeof(In))) < 4 ? 4 : (16 / int(sizeof(In)));
+        constexpr int in_al = int(sizeof(In)) * ITEMS >= 16 ? 16 : int(sizeof(In)) * ITEMS;
+        constexpr int out_al = int(sizeof(Out)) * ITEMS >= 16 ? 16 : int(sizeof(Out)) * ITEMS;
+        const int in_vec = (xa % in_al == 0) && ((n * int64_t(sizeof(In))) % in_al == 0);
+        const int out_vec = (ya % out_al == 0) && ((n * int64_t(sizeof(Out))) % out_al == 0);
+        if (n > 32 * ITEMS * 2) {       // long lines: a block per line
+            const unsigned grid = unsigned(std::min<int64_t>(outer, int64_t(sm_count) * 8));
+            scan_lines_kernel<In, Acc, Out, Op, 256, ITEMS><<<grid, 256, 0, s>>>(x, y, outer, n, in_vec, out_vec);
+        } else {                        // short lines: a warp per line
+            const unsigned grid = unsigned(std::min<int64_t>((outer + 7) / 8, int64_t(sm_count) * 8));
+            scan_lines_kernel<In, Acc, Out, Op, 32, ITEMS><<<grid, 256, 0, s>>>(x, y, outer, n, in_vec, out_vec);
+        }
+    } else {
+        constexpr int V = axis_vec<In, Out>();
+        constexpr int in_al = int(sizeof(In)) * V >= 16 ? 16 : int(sizeof(In)) * V;
+        constexpr int out_al = int(sizeof(Out)) * V >= 16 ? 16 : int(sizeof(Out)) * V;
+        const bool vec = V > 1 && inner % V == 0 && xa % in_al == 0 && ya % out_al == 0;
+        const int64_t S = axis_split(outer, n, inner, sm_count);
+        const int64_t seg = (n + S - 1) / S;
+        const int64_t cols = outer * S * (vec ? inner / V : inner);
+        const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>((cols + 255) / 256, int64_t(sm_count) * 8)));
+        Acc* tot = static_cast<Acc*>(ws);
+        if (S > 1) {
+            if (ws_bytes < size_t(outer * S * inner) * sizeof(Acc) || !ws)
+                return fail(B200_E_WORKSPACE, "scan_axis workspace %zu < %zu", ws_bytes, size_t(outer * S * inner) * sizeof(Acc));
+            // tot is Acc-aligned (caller workspace is 256-byte aligned); vector access to it needs V * sizeof(Acc) <= 16
+            if (vec) scan_cols_kernel<In, Acc, Out, Op, V, 8, 1><<<grid, 256, 0, s>>>(x, y, outer, n, inner, S, seg, tot);
+            else scan_cols_kernel<In, Acc, Out, Op, 1, 8, 1><<<grid, 256, 0, s>>>(x, y, outer, n, inner, S, seg, tot);
+            const int64_t tcols = outer * inner;
+            const unsigned tgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>((tcols + 255) / 256, int64_t(sm_count) * 8)));
+            scan_cols_kernel<Acc, Acc, Acc, Op, 1, 8, 0><<<tgrid, 256, 0, s>>>(tot, tot, outer, S, inner, 1, S, nullptr);
+            if (vec) scan_cols_kernel<In, Acc, Out, Op, V, 8, 2><<<grid, 256, 0, s>>>(x, y, outer, n, inner, S, seg, tot);
+            else scan_cols_kernel<In, Acc, Out, Op, 1, 8, 2><<<grid, 256, 0, s>>>(x, y, outer, n, inner, S, seg, tot);
+        } else {
+            if (vec) scan_cols_kernel<In, Acc, Out, Op, V, 8, 0><<<grid, 256, 0, s>>>(x, y, outer, n, inner, 1, n, nullptr);
+            else scan_cols_kernel<In, Acc, Out, Op, 1, 8, 0><<<grid, 256, 0, s>>>(x, y, outer, n, inner, 1, n, nullptr);
+        }
+    }
+    B200_CUDA_TRY(cudaPeekAtLastError());
+    return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" __attribute__((visibility("default"))) int b200_scan_axis_workspace_bytes(int64_t outer, int64_t n, int64_t inner,
+                                                                                      size_t* bytes) {
+    if (!bytes || outer < 0 || n < 0 || inner < 0) return fail(B200_E_INVALID, "bad argument");
+    DeviceInfo di;
+    int st = device_info(&di);
+    if (st) return st;
+    const int64_t S = (outer == 0 || n == 0 || inner == 0) ? 1 : axis_split(outer, n, inner, di.sm_count);
+    *bytes = S > 1 ? size_t(outer * S * inner) * 8 : 0;      // widest accumulator
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int b200_scan_axis_run(int op, int in_dtype, int out_dtype, const void* x, void* y,
+                                                                          int64_t outer, int64_t n, int64_t inner,
+                                                                          void* workspace, size_t workspace_bytes, void* stream) {
+    if (op != B200_OP_CUMSUM && op != B200_OP_CUMPROD) return fail(B200_E_INVALID, "op code %d is not a scan", op);
+    if (outer < 0 || n < 0 || inner < 0) return fail(B200_E_INVALID, "negative extent");
+    if (outer == 0 || n == 0 || inner == 0) return 0;
+    if (!x || !y) return fail(B200_E_INVALID, "null pointer");
+    DeviceInfo di;
+    int st = device_info(&di);
+    if (st) return st;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define X(I, O, TI, TA, TO)                                                                        \
+    if (in_dtype == I && out_dtype == O)                                                           \
+        return op == B200_OP_CUMSUM                                                                \
+                   ? run_axis<TI, TA, TO, ScanSum>(x, y, outer, n, inner, workspace, workspace_bytes, di.sm_count, s)  \
+                   : run_axis<TI, TA, TO, ScanProd>(x, y, outer, n, inner, workspace, workspace_bytes, di.sm_count, s);
+    B200_SCAN_TABLE(X)
+#undef X
+    return fail(B200_E_UNSUPPORTED, "no prebuilt scan for dtypes %d -> %d", in_dtype, out_dtype);
+}

@@ -203,6 +203,17 @@ int b200_scan_workspace_bytes(int64_t n, int out_dtype, size_t* bytes);
 int b200_scan_run(int op, int in_dtype, int out_dtype, const void* x, void* y, int64_t n,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* cumsum / cumprod along one axis of a dense array x[outer][n][inner] (C order; scans n), dtype
+ * conversion fused into the load, result y in the same layout.  Replaces _proc_as_batch +
+ * _batch_scan_op (cupy/_core/_routines_math.pyx:499-699: two transposing copies + log2(n) passes)
+ * with one pass.  Same dtype table as b200_scan_supported.  A workspace is needed only when
+ * outer * inner columns cannot fill the GPU and n is cut into segments (segment totals);
+ * it does not have to be zeroed. */
+int b200_scan_axis_workspace_bytes(int64_t outer, int64_t n, int64_t inner, size_t* bytes);
+int b200_scan_axis_run(int op, int in_dtype, int out_dtype, const void* x, void* y,
+                       int64_t outer, int64_t n, int64_t inner,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- JIT of user code strings (NVRTC -> cubin -> module -> function) */
 int  b200_jit_compile(const char* source, const char* name, int n_options,
                       const char* const* options, void** image, size_t* image_bytes);

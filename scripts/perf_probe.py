@@ -154,6 +154,19 @@ def main():
         del sq, sqo
         del base, xt, out, tmp
         torch.cuda.empty_cache()
+    if 'axis' in which:
+        m = 16384
+        xf = cp.from_torch(randn((m, m), torch.float32)); yf = cp.empty((m, m), np.float32)
+        report('cumsum axis=1 f32 16384^2', 8 * m * m, lambda: cp.cumsum(xf, axis=1, out=yf), iters=10)
+        report('cumsum axis=0 f32 16384^2', 8 * m * m, lambda: cp.cumsum(xf, axis=0, out=yf), iters=10)
+        x3 = xf.reshape(1024, 1024, 256); y3 = yf.reshape(1024, 1024, 256)
+        report('cumsum axis=1 f32 1024x1024x256', 8 * m * m, lambda: cp.cumsum(x3, axis=1, out=y3), iters=10)
+        report('cumsum axis=2 f32 1024x1024x256', 8 * m * m, lambda: cp.cumsum(x3, axis=2, out=y3), iters=10)
+        xi = cp.from_torch(torch.randint(-100, 100, (m, m), device='cuda', dtype=torch.int32)); yi = cp.empty((m, m), np.int64)
+        report('cumsum axis=1 int32->int64 16384^2', 12 * m * m, lambda: cp.cumsum(xi, axis=1, out=yi), iters=10)
+        report('torch cumsum dim=1 f32 16384^2', 8 * m * m, lambda: torch.cumsum(xf.to_torch(), 1), iters=5)
+        report('torch cumsum dim=0 f32 16384^2', 8 * m * m, lambda: torch.cumsum(xf.to_torch(), 0), iters=5)
+        del xf, yf, xi, yi
     if 'scan' in which:
         xi = cp.from_torch(torch.randint(-(1 << 20), 1 << 20, (n,), device='cuda', dtype=torch.int64))
         yo = cp.empty((n,), np.int64)
