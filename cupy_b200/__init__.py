@@ -21,6 +21,8 @@ from cupy_b200._core._routines_math import (  # noqa: F401
 from cupy_b200._core._routines_statistics import (  # noqa: F401
     amax, amin, argmax, argmin, mean, var, std)
 
+from cupy_b200._core._routines_more import (  # noqa: F401,E402
+    all, any, count_nonzero, nansum, nanprod, nanmin, nanmax, nanargmin, nanargmax, ptp)
 from cupy_b200 import cuda  # noqa: F401,E402
 from cupy_b200._core.fusion import fuse  # noqa: F401,E402
 

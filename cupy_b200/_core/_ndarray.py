@@ -630,6 +630,18 @@ class ndarray:
         from cupy_b200._core import _routines_statistics as s
         return s._ndarray_std(self, axis, dtype, out, ddof, keepdims)
 
+    def all(self, axis=None, out=None, keepdims=False):
+        from cupy_b200._core import _routines_more as r
+        return r.all(self, axis, out, keepdims)
+
+    def any(self, axis=None, out=None, keepdims=False):
+        from cupy_b200._core import _routines_more as r
+        return r.any(self, axis, out, keepdims)
+
+    def ptp(self, axis=None, out=None, keepdims=False):
+        from cupy_b200._core import _routines_more as r
+        return r.ptp(self, axis, out, keepdims)
+
 
 # ---- creation ------------------------------------------------------------------------
 def empty(shape, dtype=float, order='C'):
