@@ -51,6 +51,24 @@ def _functor_source(kernel, in_args, in_params, out_args, out_params, type_map, 
     lines.append(kernel.preamble)
     lines.append('typedef %s _type_reduce;' % reduce_type)
     lines.append('static_assert(sizeof(_type_reduce) <= %d, "reduce_type too large");' % _MAX_ACC_BYTES)
+    multi = [a for a in in_args if isinstance(a, ndarray)] if structured else []
+    if len(multi) > 1:
+        ts = [get_typename(a.dtype) for a in multi]
+        k_all = range(len(multi))
+        lines.append('struct __align__(16) _In { %s };' % ' '.join('%s m%d;' % (t, k) for k, t in enumerate(ts)))
+        lines.append('struct _InPtr {')
+        lines.append('  ' + ' '.join('const %s* p%d;' % (t, k) for k, t in enumerate(ts)))
+        lines.append('  __device__ __forceinline__ _InPtr operator+(long long _o) const { _InPtr _r; %s return _r; }'
+                     % ' '.join('_r.p%d = p%d + _o;' % (k, k) for k in k_all))
+        lines.append('  __device__ __forceinline__ _In operator[](long long _i) const { _In _r; %s return _r; }'
+                     % ' '.join('_r.m%d = p%d[_i];' % (k, k) for k in k_all))
+        lines.append('};')
+        lines.append('template <int _N> __device__ __forceinline__ void load_pack(b200::Pack<_In, _N>& _d, const _InPtr& _p) {')
+        for k, t in enumerate(ts):
+            lines.append('  { b200::Pack<%s, _N> _t; b200::load_pack(_t, _p.p%d);' % (t, k))
+            lines.append('#pragma unroll')
+            lines.append('    for (int _i = 0; _i < _N; ++_i) _d[_i].m%d = _t[_i]; }' % k)
+        lines.append('}')
     lines.append('struct _Op {')
     lines.append('  typedef _type_reduce acc_t; typedef IndexT index_t; struct ctx_t {};')
     lines.append('  static constexpr bool kWideIndex = false;')
@@ -91,11 +109,22 @@ def _functor_source(kernel, in_args, in_params, out_args, out_params, type_map, 
     lines.append('    %s;' % post_map_expr)
     lines.append('  }')
     if structured:
-        in_arr = [a for a in in_args if isinstance(a, ndarray)][0]
-        lines.append('  typedef %s in_t; typedef %s out_t;' % (get_typename(in_arr.dtype), get_typename(out_args[0].dtype)))
-        lines.append('  __device__ ctx_t step(int) const { return ctx_t(); }')
-        lines.append('  __device__ acc_t single(const in_t& _v, index_t _j) const {'
-                     ' const char* _q = reinterpret_cast<const char*>(&_v); return map_at(&_q, _j); }')
+        in_arrs = [a for a in in_args if isinstance(a, ndarray)]
+        if len(in_arrs) == 1:
+            lines.append('  typedef %s in_t; typedef %s out_t;'
+                         % (get_typename(in_arrs[0].dtype), get_typename(out_args[0].dtype)))
+            lines.append('  __device__ ctx_t step(int) const { return ctx_t(); }')
+            lines.append('  __device__ acc_t single(const in_t& _v, index_t _j) const {'
+                         ' const char* _q = reinterpret_cast<const char*>(&_v); return map_at(&_q, _j); }')
+        else:
+            # several arrays of one layout: the skeleton streams a tuple of their elements (_In) through
+            # a struct of pointers (_InPtr), see b200::in_ptr in reduce.cuh
+            lines.append('  typedef _In in_t; typedef _InPtr ptr_t; typedef %s out_t;' % get_typename(out_args[0].dtype))
+            lines.append('  __device__ ctx_t step(int) const { return ctx_t(); }')
+            lines.append('  __device__ acc_t single(const in_t& _v, index_t _j) const { const char* _q[%d] = {%s};'
+                         ' return map_at(_q, _j); }'
+                         % (len(in_arrs), ', '.join('reinterpret_cast<const char*>(&_v.m%d)' % k
+                                                    for k in range(len(in_arrs)))))
         lines.append('  __device__ void accumulate(acc_t& _acc, const ctx_t&, const in_t& _v, index_t _j) const {'
                      ' _acc = combine(_acc, single(_v, _j)); }')
         lines.append('  __device__ out_t post(const acc_t& _a, long long) const {'
@@ -127,9 +156,12 @@ def _sm_count():
 
 
 def _pick_vec(ptr, inner, itemsize, full):
+    """`ptr` / `itemsize` may be lists (several operands of one layout): every one must be aligned."""
+    ptrs = ptr if isinstance(ptr, (list, tuple)) else [ptr]
+    sizes = itemsize if isinstance(itemsize, (list, tuple)) else [itemsize] * len(ptrs)
     vec = full
     while vec > 1:
-        if ptr % (vec * itemsize) == 0 and inner % vec == 0:
+        if inner % vec == 0 and all(q % min(vec * sz, 16) == 0 for q, sz in zip(ptrs, sizes)):
             break
         vec >>= 1
     return vec
@@ -137,8 +169,9 @@ def _pick_vec(ptr, inner, itemsize, full):
 
 def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_map,
                       map_expr, reduce_expr, post_map_expr, reduce_type, stream):
-    x = [a for a in in_args if isinstance(a, ndarray)][0]
-    isz = x.dtype.itemsize
+    xs = [a for a in in_args if isinstance(a, ndarray)]
+    x = xs[0]
+    isz = max(a.dtype.itemsize for a in xs)          # the widest operand sets the vector width
     acc_size = _acc_size(reduce_type, type_map)
     known = acc_size is not None
     acc_bytes = acc_size if known else _MAX_ACC_BYTES
@@ -151,7 +184,7 @@ def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_ma
     grid = (1, 1, 1)
     ws_need = 0
     if kind == _lib.RED_FULL:
-        vec = _pick_vec(x.ptr, layout.n_reduce, isz, full_vec)
+        vec = _pick_vec([a.ptr for a in xs], layout.n_reduce, [a.dtype.itemsize for a in xs], full_vec)
         vec = vec if vec == full_vec else 1
         tile = _THREADS * vec * unroll
         g = max(1, min((layout.n_reduce + tile - 1) // tile, sm * 8))
@@ -162,7 +195,7 @@ def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_ma
                 'reinterpret_cast<_Op::acc_t*>(p.ws0), reinterpret_cast<uint32_t*>(p.ws1));' % (vec, unroll, _THREADS))
         tag = 'full_v%d' % vec
     elif kind == _lib.RED_ROWS:
-        vec = _pick_vec(x.ptr, layout.n_reduce, isz, full_vec)
+        vec = _pick_vec([a.ptr for a in xs], layout.n_reduce, [a.dtype.itemsize for a in xs], full_vec)
         vec = vec if vec == full_vec else 1
         n = layout.n_reduce
         group = _THREADS if n >= 2048 else 32 if n >= 32 * vec else 8 if n >= 8 * vec else 1
@@ -176,7 +209,7 @@ def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_ma
         cv = full_vec
         while cv > 1 and 8 * 32 * cv * acc_bytes > 32768:
             cv >>= 1
-        vec = _pick_vec(x.ptr, layout.n_out, isz, cv)
+        vec = _pick_vec([a.ptr for a in xs], layout.n_out, [a.dtype.itemsize for a in xs], cv)
         vec = vec if vec == cv else 1
         ru = 2 if vec >= 8 else 4
         tiles = (layout.n_out + 32 * vec - 1) // (32 * vec)
@@ -190,7 +223,7 @@ def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_ma
                 'reinterpret_cast<_Op::acc_t*>(p.ws0), reinterpret_cast<uint32_t*>(p.ws1));' % (vec, ru))
         tag = 'cols_v%d' % vec
 
-    key = ('s', tag, index64, x.dtype.char, out.dtype.char, type_map, reduce_type,
+    key = ('s', tag, index64, tuple(a.dtype.char for a in xs), out.dtype.char, type_map, reduce_type,
            tuple(a.descr.char for a in in_args if isinstance(a, CScalar)))
     fn = kernel._memo.get(key)
     name = kernel.name + '_' + tag
@@ -198,7 +231,7 @@ def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_ma
         src = _functor_source(kernel, in_args, kernel.in_params, [out], kernel.out_params, type_map,
                               map_expr, reduce_expr, post_map_expr, reduce_type, index64, True)
         src += '''
-struct _Params { _Op op; const _Op::in_t* x; _Op::out_t* y; long long a0, a1, a2; void* ws0; void* ws1; };
+struct _Params { _Op op; b200::in_ptr<_Op>::type x; _Op::out_t* y; long long a0, a1, a2; void* ws0; void* ws1; };
 extern "C" __global__ void __launch_bounds__(%d) %s(const __grid_constant__ _Params p) {
   %s
 }
@@ -208,7 +241,8 @@ extern "C" __global__ void __launch_bounds__(%d) %s(const __grid_constant__ _Par
         kernel._memo[key] = fn
     ws_ptr, ws_bytes = _workspace.get(ws_need, stream)
     params = _pack_op(in_args, layout.n_reduce * layout.n_out * layout.batch, layout.n_out * layout.batch)
-    params += struct.pack('<QQqqqQQ', x.ptr, out.ptr, a0, a1, a2, ws_ptr + _TICKET_BYTES, ws_ptr)
+    params += b''.join(struct.pack('<Q', a.ptr) for a in xs)
+    params += struct.pack('<QqqqQQ', out.ptr, a0, a1, a2, ws_ptr + _TICKET_BYTES, ws_ptr)
     _launch(fn, grid, _THREADS, params, stream)
 
 

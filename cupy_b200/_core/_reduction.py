@@ -169,12 +169,19 @@ class _AbstractReductionKernel:
         n_out = _prod(a_shape[i] for i in out_axis)
 
         arrays = [a for a in in_args if isinstance(a, ndarray)]
-        single = (len(arrays) == 1 and len(out_args) == 1
-                  and not any(p.raw for p in self.in_params + self.out_params))
+        # structured kernels stream one operand -- or several arrays that share ONE layout (same
+        # shape and element strides after broadcasting), as a tuple of their elements
+        x0 = arrays[0] if arrays else None
+        uniform = (len(arrays) >= 1 and len(out_args) == 1
+                   and not any(p.raw for p in self.in_params + self.out_params)
+                   and all(a.shape == x0.shape
+                           and tuple(t // a.dtype.itemsize for t in a.strides) == tuple(t // x0.dtype.itemsize for t in x0.strides)
+                           and all(t % a.dtype.itemsize == 0 for t in a.strides)
+                           for a in arrays))
+        single = uniform and len(arrays) == 1
         layout = Layout(-1, 1, n_reduce, n_out)
-        if single and n_reduce > 0:
-            x = arrays[0]
-            layout = _classify(x.shape, x.strides, x.dtype.itemsize, reduce_axis, out_axis, self._ordered_index)
+        if uniform and n_reduce > 0:
+            layout = _classify(x0.shape, x0.strides, x0.dtype.itemsize, reduce_axis, out_axis, self._ordered_index)
 
         # the fast layouts write a dense C-ordered result of the loop's natural dtype
         out = out_args[0]
@@ -203,7 +210,7 @@ class _AbstractReductionKernel:
                         _kernel.elementwise_copy(target.reshape(out.shape), out)
                     return ret
             # ---- NVRTC functor on the same skeleton
-            if single:
+            if uniform:
                 _codegen_reduce.launch_structured(
                     self, layout, in_args, target, in_types, out_types, type_map,
                     map_expr, reduce_expr, post_map_expr, reduce_type, st)

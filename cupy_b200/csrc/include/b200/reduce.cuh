@@ -25,6 +25,14 @@
 
 namespace b200 {
 
+// The input "pointer" of a skeleton: `const in_t*` unless the functor brings its own type
+// (Op::ptr_t).  NVRTC-generated functors of reductions over SEVERAL arrays of one common layout
+// use a struct of pointers whose in_t is the tuple of their elements: it only has to offer
+// `p + offset`, `p[i]` and a `load_pack(Pack<in_t, N>&, p)` overload.
+template <class T> struct void_of { typedef void type; };
+template <class Op, class = void> struct in_ptr { typedef const typename Op::in_t* __restrict__ type; };
+template <class Op> struct in_ptr<Op, typename void_of<typename Op::ptr_t>::type> { typedef typename Op::ptr_t type; };
+
 template <class T>
 B200_DEVICE T load_volatile(const T* p) {
     // accumulators published by other blocks: read around L1, in words when possible
@@ -119,7 +127,7 @@ struct ThreadAcc {
 // ---------------------------------------------------------------------------
 template <class Op, int VEC, int UNROLL, int THREADS>
 __device__ __forceinline__ void reduce_full_body(
-        const Op& op, const typename Op::in_t* __restrict__ x, typename Op::out_t* __restrict__ y,
+        const Op& op, typename in_ptr<Op>::type x, typename Op::out_t* __restrict__ y,
         int64_t n, typename Op::acc_t* partials, uint32_t* ticket) {
     typedef typename Op::acc_t acc_t;
     typedef typename Op::index_t index_t;
@@ -176,7 +184,7 @@ __device__ __forceinline__ void reduce_full_body(
 // ---------------------------------------------------------------------------
 template <class Op, int VEC, int UNROLL, int THREADS, int GROUP>
 __device__ __forceinline__ void reduce_rows_body(
-        const Op& op, const typename Op::in_t* __restrict__ x, typename Op::out_t* __restrict__ y,
+        const Op& op, typename in_ptr<Op>::type x, typename Op::out_t* __restrict__ y,
         int64_t rows, int64_t n) {
     typedef typename Op::acc_t acc_t;
     typedef typename Op::index_t index_t;
@@ -192,7 +200,7 @@ __device__ __forceinline__ void reduce_rows_body(
          row0 += int64_t(gridDim.x) * kRowsPerBlock) {
         const int64_t row = row0 + gi;
         const bool live = row < rows;
-        const typename Op::in_t* __restrict__ xr = x + (live ? row : 0) * n;
+        const typename in_ptr<Op>::type xr = x + (live ? row : 0) * n;
         ThreadAcc<Op, UNROLL, VEC> ta(op);
         if (live) {
             int64_t base = 0;
@@ -228,7 +236,7 @@ __device__ __forceinline__ void reduce_rows_body(
 // ---------------------------------------------------------------------------
 template <class Op, int VEC, int RU>
 __device__ __forceinline__ void reduce_cols_body(
-        const Op& op, const typename Op::in_t* __restrict__ x, typename Op::out_t* __restrict__ y,
+        const Op& op, typename in_ptr<Op>::type x, typename Op::out_t* __restrict__ y,
         int64_t n, int64_t cols, typename Op::acc_t* partials, uint32_t* tickets) {
     typedef typename Op::acc_t acc_t;
     typedef typename Op::index_t index_t;
@@ -246,7 +254,7 @@ __device__ __forceinline__ void reduce_cols_body(
     const int64_t rows_per_split = (n + nsplit - 1) / nsplit;
     const int64_t r_begin = int64_t(split) * rows_per_split;
     const int64_t r_end = (r_begin + rows_per_split < n) ? r_begin + rows_per_split : n;
-    const typename Op::in_t* __restrict__ xb = x + b * n * cols + c0;
+    const typename in_ptr<Op>::type xb = x + b * n * cols + c0;
 
     ThreadAcc<Op, RU, VEC> ta(op);
     if (col_ok) {

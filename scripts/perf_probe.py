@@ -154,6 +154,16 @@ def main():
         del sq, sqo
         del base, xt, out, tmp
         torch.cuda.empty_cache()
+    if 'multi' in which:
+        m = 16384
+        xa = cp.from_torch(randn((m, m), torch.float32)); xb = cp.from_torch(randn((m, m), torch.float32))
+        dot = cp.ReductionKernel('T x, T y', 'T z', 'x * y', 'a + b', 'z = a', '0', 'dot')
+        for ax in (None, 1, 0):
+            report('ReductionKernel dot(x,y) axis=%s f32 16384^2' % ax, 8 * m * m, lambda: dot(xa, xb, axis=ax), iters=10)
+        fr = cp.fuse(kernel_name='fuse_sqdiff')(lambda x, y: cp.sum((x - y) * (x - y), axis=1))
+        report('cupy_b200.fuse sum((x-y)^2, axis=1) 16384^2', 8 * m * m, lambda: fr(xa, xb), iters=10)
+        report('torch (x*y).sum(1) 16384^2 (2 kernels)', 8 * m * m, lambda: (xa.to_torch() * xb.to_torch()).sum(1), iters=5)
+        del xa, xb
     if 'axis' in which:
         m = 16384
         xf = cp.from_torch(randn((m, m), torch.float32)); yf = cp.empty((m, m), np.float32)

@@ -283,8 +283,11 @@ def test_reduction_routes(dry):
     assert dry[-1]['kind'] == 'jit_reduce' and 'rows' in dry[-1]['name']
     a[::2].sum(axis=0)                                  # strided -> generic kernel
     assert 'generic' in dry[-1]['name']
-    cp.ReductionKernel('T x, T y', 'T z', 'x * y', 'a + b', 'z = a', '0', 'dot')(a, a, axis=1)
-    assert 'generic' in dry[-1]['name']                 # two array operands
+    dot = cp.ReductionKernel('T x, T y', 'T z', 'x * y', 'a + b', 'z = a', '0', 'dot')
+    dot(a, a, axis=1)                                   # two arrays of ONE layout: structured, tuple operand
+    assert 'rows' in dry[-1]['name'] and '_InPtr' in dry[-1].get('source', '_InPtr')
+    dot(a, a[0], axis=1)                                # a broadcast operand has another layout -> generic kernel
+    assert 'generic' in dry[-1]['name']
 
 
 def test_reduction_kernel_errors(dry):

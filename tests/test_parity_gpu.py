@@ -505,3 +505,44 @@ def test_streams_events_and_async_get_set(cp):
     with pytest.raises(TypeError):
         dx.get(out=np.empty(n, np.float64))
     np.testing.assert_array_equal(dx.reshape(1024, 1024).get(out=np.empty((1024, 1024), np.float32)), hx.reshape(1024, 1024))
+
+
+@pytest.mark.parametrize('shape,axis', [((1 << 20,), None), ((300, 1000), 1), ((300, 1000), 0), ((7, 65, 33), (0, 2)),
+                                        ((4, 5, 2048), 2), ((1000, 3), 1), ((3, 70000), 1), ((5, 7, 9), None)])
+def test_reduction_kernel_several_arrays_one_layout(cp, shape, axis):
+    """Multi-operand ReductionKernels (the reference's dot / weighted-sum pattern,
+    tests/cupy_tests/core_tests/test_reduction.py, test_userkernel.py) on the structured
+    skeletons: the operands travel as a tuple through one pointer struct."""
+    x, y = rnd(shape, 'float32'), rnd(shape, 'float32')
+    dot = cp.ReductionKernel('T x, T y', 'T z', 'x * y', 'a + b', 'z = a', '0', 'dot2')
+    got = dot(cp.asarray(x), cp.asarray(y), axis=axis).get()
+    want = (x.astype(np.float64) * y).sum(axis=axis)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-3)
+    # mixed item sizes (float32, int8 weights, float64 scale) + a scalar parameter + keepdims
+    w = rnd(shape, 'int8')
+    s = rnd(shape, 'float64')
+    k = cp.ReductionKernel('float32 x, int8 w, float64 s, float64 c', 'float64 z', 'x * w * s + c', 'a + b', 'z = a', '0',
+                           'weighted3', reduce_type='double')
+    got = k(cp.asarray(x), cp.asarray(w), cp.asarray(s), 0.5, axis=axis, keepdims=True).get()
+    want = ((x * w.astype(np.float32)).astype(np.float64) * s + 0.5).sum(axis=axis, keepdims=True)   # x * w is a float32 product in C++
+    np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-7)      # float32 product rounding + summation order
+    # arg-style reduction over two arrays: index of the largest |x - y|
+    am = cp.ReductionKernel(
+        'T x, T y', 'int64 z', 'min_max_st<float>(fabsf(x - y), _J)', 'my_argmax_float(a, b)', 'z = a.index', None,
+        'argmax_absdiff', reduce_type='min_max_st<float>', preamble=_mm_preamble(cp))
+    if axis is None or isinstance(axis, int):
+        got = am(cp.asarray(x), cp.asarray(y), axis=axis).get()
+        np.testing.assert_array_equal(got, np.abs(x - y).argmax(axis=axis))
+    # transposed (non C-order but common layout) and strided views fall back correctly
+    if len(shape) == 2:
+        got = dot(cp.asarray(x).T, cp.asarray(y).T, axis=0).get()
+        np.testing.assert_allclose(got, (x.T.astype(np.float64) * y.T).sum(axis=0), rtol=1e-4, atol=1e-3)
+        got = dot(cp.asarray(x)[::2], cp.asarray(y)[::2], axis=1).get()
+        np.testing.assert_allclose(got, (x[::2].astype(np.float64) * y[::2]).sum(axis=1), rtol=1e-4, atol=1e-3)
+        got = dot(cp.asarray(x), cp.asarray(y[0]), axis=1).get()                 # broadcast operand -> generic kernel
+        np.testing.assert_allclose(got, (x.astype(np.float64) * y[0]).sum(axis=1), rtol=1e-4, atol=1e-3)
+
+
+def _mm_preamble(cp):
+    from cupy_b200._core import _routines_statistics
+    return _routines_statistics._min_max_preamble
