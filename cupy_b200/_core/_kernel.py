@@ -20,6 +20,7 @@ string is wrapped in the tiler glue of `_codegen.py` and compiled by NVRTC.
 from __future__ import annotations
 
 import ctypes
+import re as _re
 import string
 import threading
 
@@ -293,7 +294,7 @@ def _collapse_for_abi(a):
     raise NotImplementedError('arrays with more than %d dimensions are not supported' % _lib.MAX_NDIM)
 
 
-def plan_elementwise(args, params, n_in, loop_shape):
+def plan_elementwise(args, params, n_in, loop_shape, keep_order=True):
     ops = _make_operands(args, params, n_in, loop_shape)
     plan = _lib.EwPlan()
     if not any(o.kind == _lib.KIND_ARRAY for o in ops):
@@ -306,7 +307,7 @@ def plan_elementwise(args, params, n_in, loop_shape):
         plan.size = _prod(loop_shape)
         plan.shape[0] = plan.size
         return ops, plan
-    _lib.check(_lib.lib.b200_ew_plan(len(args), ops, ctypes.byref(plan)))
+    _lib.check(_lib.lib.b200_ew_plan_ex(len(args), ops, _lib.PLAN_KEEP_ORDER if keep_order else 0, ctypes.byref(plan)))
     return ops, plan
 
 
@@ -438,6 +439,9 @@ class ElementwiseKernel:
         names = [p.name for p in self.params]
         if 'i' in names:
             raise ValueError('Can not use \'i\' as a parameter name')
+        # the loop order is free unless the code can observe the C-order linear index
+        text = ' '.join((operation, kwargs.get('loop_prep', ''), kwargs.get('after_loop', '')))
+        self._keeps_order = (any(p.raw for p in self.params) or _re.search(r'\b(i|_ind)\b', text) is not None)
         self._params_type_memo = {}
         self._cached_codes = {}
         self._spec = _codegen.EwSpec(
@@ -488,7 +492,7 @@ class ElementwiseKernel:
             if isinstance(x, CScalar):
                 x.apply_dtype(in_types[i])
         inout_args = in_args + out_args
-        ops, plan = plan_elementwise(inout_args, self.params, self.nin, shape)
+        ops, plan = plan_elementwise(inout_args, self.params, self.nin, shape, keep_order=self._keeps_order)
         # the 128-thread default of the reference is a floor for its scalar loop;
         # the tilers are built for 256 -- a caller's explicit block_size is honoured
         bs = None if block_size == 128 else block_size
@@ -687,6 +691,9 @@ class ufunc:
         self._params_with_where = self._params[:nin] + (ParameterInfo('T _where', True),) + self._params[nin:]
         self._routine_cache = {}
         self._specs = {}
+        # ufunc routines that read the loop index `i` (none of the built-ins) pin the loop order
+        self._keeps_order = any(isinstance(op.routine, str) and _re.search(r'\b(i|_ind)\b', op.routine)
+                                for op in ops.ops) or bool(_re.search(r'\b(i|_ind)\b', loop_prep or ''))
 
     def __repr__(self):
         return '<ufunc \'%s\'>' % self.name
@@ -766,7 +773,7 @@ class ufunc:
         all_args = in_args + where_args + out_args
         params = self._params_with_where if has_where else self._params
         n_in = self.nin + len(where_args)
-        ops, plan = plan_elementwise(all_args, params, n_in, shape)
+        ops, plan = plan_elementwise(all_args, params, n_in, shape, keep_order=self._keeps_order)
         st = current_stream_ptr()
 
         # ---- prebuilt kernel?

@@ -30,6 +30,7 @@ OP_SUM, OP_MIN, OP_MAX, OP_ARGMIN, OP_ARGMAX, OP_CUMSUM, OP_CUMPROD, OP_PROD, \
 OK, E_INVALID, E_UNSUPPORTED, E_WORKSPACE, E_NOLIB, E_COMPILE = 0, -1, -2, -3, -4, -5
 
 KIND_ARRAY, KIND_SCALAR, KIND_RAW = 0, 1, 2
+PLAN_KEEP_ORDER = 1
 EW_FLAT, EW_ROWWISE, EW_TILED, EW_TILED_TMA, EW_TILED_REG = 0, 1, 2, 3, 4
 RED_FULL, RED_ROWS, RED_COLS = 0, 1, 2
 
@@ -103,6 +104,7 @@ _EXPORTS = {
     'b200_device_info': (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     'b200_dtype_itemsize': (c_int, [c_int]),
     'b200_ew_plan': (c_int, [c_int, POINTER(Operand), POINTER(EwPlan)]),
+    'b200_ew_plan_ex': (c_int, [c_int, POINTER(Operand), c_uint32, POINTER(EwPlan)]),
     'b200_ufunc_supported': (c_int, [c_int, c_int, POINTER(c_int32), c_int32]),
     'b200_ufunc_launch': (c_int, [c_int, POINTER(EwPlan), c_int, POINTER(Operand), c_void_p]),
     'b200_reduce_supported': (c_int, [POINTER(ReduceDesc)]),

@@ -211,7 +211,18 @@ extern "C" __attribute__((visibility("default"))) int b200_device_info(int* sm_c
     return 0;
 }
 
+static int plan_impl(int nargs, const b200_operand_t* args, uint32_t flags, b200_ew_plan_t* plan);
+
 extern "C" __attribute__((visibility("default"))) int b200_ew_plan(int nargs, const b200_operand_t* args, b200_ew_plan_t* plan) {
+    return plan_impl(nargs, args, B200_PLAN_KEEP_ORDER, plan);
+}
+
+extern "C" __attribute__((visibility("default"))) int b200_ew_plan_ex(int nargs, const b200_operand_t* args, uint32_t flags,
+                                                                       b200_ew_plan_t* plan) {
+    return plan_impl(nargs, args, flags, plan);
+}
+
+static int plan_impl(int nargs, const b200_operand_t* args, uint32_t flags, b200_ew_plan_t* plan) {
     if (!args || !plan) return fail(B200_E_INVALID, "null argument");
     if (nargs <= 0 || nargs > B200_MAX_ARGS) return fail(B200_E_INVALID, "operand count %d not in 1..%d", nargs, B200_MAX_ARGS);
     std::memset(plan, 0, sizeof(*plan));
@@ -257,6 +268,38 @@ extern "C" __attribute__((visibility("default"))) int b200_ew_plan(int nargs, co
     if (nd == 0) {  // a single element
         nd = 1; shape[0] = 1;
         for (int a = 0; a < nargs; ++a) st[a][0] = is_array(args[a]) ? dtype_size(args[a].dtype) : 0;
+    }
+    // ---- loop order: a kernel that never observes the C-order linear index may walk the dims in any
+    //      order, so sort them by the (first) output's stride, largest first -- F-ordered / permuted
+    //      operands then collapse and vectorise exactly like C-ordered ones
+    if (!(flags & B200_PLAN_KEEP_ORDER) && nd > 1) {
+        int ref = -1;
+        for (int a = 0; a < nargs && ref < 0; ++a)
+            if (is_array(args[a]) && args[a].is_output) ref = a;
+        if (ref < 0) ref = first;
+        int order[B200_MAX_NDIM];
+        for (int d = 0; d < nd; ++d) order[d] = d;
+        auto key2 = [&](int d) {
+            int64_t m = 0;
+            for (int a = 0; a < nargs; ++a)
+                if (is_array(args[a])) m = std::max<int64_t>(m, std::llabs(st[a][d]));
+            return m;
+        };
+        std::stable_sort(order, order + nd, [&](int x, int y) {
+            const int64_t ax = std::llabs(st[ref][x]), ay = std::llabs(st[ref][y]);
+            if (ax != ay) return ax > ay;
+            return key2(x) > key2(y);
+        });
+        int64_t shape2[B200_MAX_NDIM];
+        int64_t st2[B200_MAX_ARGS][B200_MAX_NDIM];
+        for (int d = 0; d < nd; ++d) {
+            shape2[d] = shape[order[d]];
+            for (int a = 0; a < nargs; ++a) st2[a][d] = st[a][order[d]];
+        }
+        for (int d = 0; d < nd; ++d) {
+            shape[d] = shape2[d];
+            for (int a = 0; a < nargs; ++a) st[a][d] = st2[a][d];
+        }
     }
     int w = 0;  // write cursor: dims [0..w] are final so far
     for (int d = 1; d < nd; ++d) {

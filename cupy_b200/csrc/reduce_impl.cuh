@@ -64,10 +64,17 @@ static int full_grid(int64_t n, int vec, int unroll, int sm) {
     return int(std::max<int64_t>(1, std::min<int64_t>(tiles, int64_t(sm) * 8)));
 }
 
-static int rows_group(int64_t n, int vec) {
+// threads per row: the largest group whose unrolled tile (group * vec * unroll) still fits the row,
+// so that the row is read with full vector batches and not through the scalar tail loop
+static int rows_group(int64_t n, int vec, int unroll) {
     if (n >= 2048) return kRedThreads;
-    if (n >= int64_t(32) * vec) return 32;
-    if (n >= int64_t(8) * vec) return 8;
+    if (n >= int64_t(32) * vec * unroll) return 32;
+    if (n >= int64_t(8) * vec * unroll) return 8;
+    // shorter rows: a thread per row when the row holds at least one vector batch (16-byte loads,
+    // the lines are completed from L1 by the thread's next loads); else the coalesced scalar tail loop
+    if (n >= int64_t(vec) * unroll && vec > 1) return 1;
+    if (n >= 32) return 32;
+    if (n >= 8) return 8;
     return 1;
 }
 
@@ -125,7 +132,7 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
         if (query) { *need = 0; return 0; }
         const int vec = pick_vec<FULLVEC>(x, d->n_reduce, sizeof(in_t));
         const int v = (vec == FULLVEC) ? FULLVEC : 1;
-        const int group = rows_group(d->n_reduce, v);
+        const int group = rows_group(d->n_reduce, v, U);
         const int64_t rows_per_block = kRedThreads / group;
         const int64_t blocks = (d->n_out + rows_per_block - 1) / rows_per_block;
         const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>(blocks, int64_t(di.sm_count) * 64)));

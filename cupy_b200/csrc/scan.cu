@@ -103,6 +103,10 @@ static int run_tma(int op, const void* x, void* y, int64_t n, void* wsp, size_t 
     B200_TMA_CASE(252, 256, 5, 2)
     B200_TMA_CASE(262, 256, 6, 2)
     B200_TMA_CASE(263, 256, 6, 3)
+    B200_TMA_CASE(231, 256, 3, 1)      // 96 KB: two blocks (16 warps) per SM
+    B200_TMA_CASE(131, 128, 3, 1)      // 48 KB: four blocks per SM
+    B200_TMA_CASE(142, 128, 4, 2)      // 64 KB: three blocks per SM
+    B200_TMA_CASE(431, 512, 3, 1)      // one block of 16 warps per SM
 #undef B200_TMA_CASE
     return B200_E_UNSUPPORTED;
 }

@@ -166,6 +166,12 @@ int         b200_dtype_itemsize(int dtype);
 
 /* ---- elementwise launcher */
 int b200_ew_plan(int nargs, const b200_operand_t* args, b200_ew_plan_t* plan);
+/* Same, with flags.  B200_PLAN_KEEP_ORDER: the kernel observes the C-order linear index (`i`, `_ind`, raw
+ * operands), so the loop dims keep their order (what b200_ew_plan does).  Without it the dims are sorted by
+ * the output's strides first, so F-ordered and permuted operands collapse and vectorise like C-ordered
+ * ones (the reference only collapses C-contiguous operands, cupy/_core/_kernel.pyx:360-461). */
+#define B200_PLAN_KEEP_ORDER 1u
+int b200_ew_plan_ex(int nargs, const b200_operand_t* args, uint32_t flags, b200_ew_plan_t* plan);
 int b200_ufunc_supported(int ufunc, int nin, const int32_t* in_dtypes, int32_t out_dtype);
 int b200_ufunc_launch(int ufunc, const b200_ew_plan_t* plan, int nargs,
                       const b200_operand_t* args, void* stream);

@@ -38,7 +38,7 @@ def randn(shape, dtype):
 
 
 def main():
-    which = sys.argv[1:] or ['copy', 'axpy', 'sum', 'c3', 'c4', 'scan']
+    which = sys.argv[1:] or ['copy', 'axpy', 'sum', 'c3', 'c4', 'scan', 'axis', 'multi', 'cast', 'rows']
     n = 1 << 28
     if 'copy' in which:
         a = torch.empty(n, device='cuda', dtype=torch.float32); b = torch.empty_like(a)
@@ -154,6 +154,29 @@ def main():
         del sq, sqo
         del base, xt, out, tmp
         torch.cuda.empty_cache()
+    if 'cast' in which:
+        x32 = cp.from_torch(randn((n,), torch.float32))
+        x16 = cp.from_torch(randn((n,), torch.float16))
+        xi32 = cp.from_torch(torch.randint(-100, 100, (n,), device='cuda', dtype=torch.int32))
+        report('astype f32 -> f16 2^28', 6 * n, lambda: x32.astype(np.float16), iters=10)
+        report('astype f16 -> f32 2^28', 6 * n, lambda: x16.astype(np.float32), iters=10)
+        report('astype i32 -> f64 2^28', 12 * n, lambda: xi32.astype(np.float64), iters=10)
+        report('astype f32 -> i8 2^28', 5 * n, lambda: x32.astype(np.int8), iters=10)
+        m2 = x32.reshape(16384, 16384)
+        report('ascontiguous of [:, ::2] view f32', 4 * n, lambda: m2[:, ::2].copy(), iters=10)
+        report('copy into strided out[:, ::2]', 4 * n, lambda: cp.elementwise_copy(m2[:, :8192], m2[:, ::2]), iters=10)
+        report('x.T.astype(f16) 16384^2 (transposed + cast)', 6 * n, lambda: m2.T.astype(np.float16), iters=10)
+        del x32, x16, xi32, m2
+    if 'rows' in which:
+        xs = cp.from_torch(randn((n,), torch.float32))
+        for cols in (16, 64, 128, 256, 512, 1024, 4096):
+            v2 = xs.reshape(n // cols, cols)
+            report('sum axis=1 f32 rows of %d' % cols, 4 * n, lambda: v2.sum(axis=1), iters=10)
+        v2 = xs.reshape(n // 256, 256)
+        report('max axis=1 f32 rows of 256', 4 * n, lambda: v2.max(axis=1), iters=10)
+        report('argmax axis=1 f32 rows of 256', 4 * n, lambda: v2.argmax(axis=1), iters=10)
+        report('var axis=1 f32 rows of 256', 4 * n, lambda: v2.var(axis=1), iters=10)
+        del xs, v2
     if 'multi' in which:
         m = 16384
         xa = cp.from_torch(randn((m, m), torch.float32)); xb = cp.from_torch(randn((m, m), torch.float32))
