@@ -199,3 +199,30 @@ def test_nvrtc_compiles_for_sm100a_and_reports_errors():
     with pytest.raises(_lib.CompileException) as e:
         _jit.compile_to_cubin('extern "C" __global__ void k() { undefined_symbol(); }', (), 'bad.cu')
     assert 'undefined_symbol' in str(e.value)
+
+
+def test_plan_ex_free_loop_order_collapses_f_ordered_operands():
+    # F-ordered 2-D float32 -> float16 copy (x.T.astype): both operands unit-stride along dim 0
+    shape = (4096, 2048)
+    ops = [_operand(0x100000, F32, shape, (4, 16384)), _operand(0x4000000, _lib.TYPE_FLOAT16, shape, (2, 8192), out=True)]
+    arr = (_lib.Operand * 2)(*ops)
+    keep, free = _lib.EwPlan(), _lib.EwPlan()
+    assert _lib.lib.b200_ew_plan_ex(2, arr, _lib.PLAN_KEEP_ORDER, ctypes.byref(keep)) == 0
+    assert _lib.lib.b200_ew_plan_ex(2, arr, 0, ctypes.byref(free)) == 0
+    assert keep.variant == _lib.EW_ROWWISE and keep.ndim == 2           # the linear index pins the order
+    assert free.variant == _lib.EW_FLAT and free.ndim == 1 and free.vec == 4 and free.size == 4096 * 2048
+    # b200_ew_plan is the order-keeping form
+    s, p = _plan(ops)
+    assert s == 0 and p.variant == keep.variant and p.ndim == keep.ndim
+    # C-ordered inputs into an F-ordered output: sorted by the OUTPUT's strides -> the inputs are the transposed ones
+    ops = [_operand(0x100000, F32, shape, (8192, 4)), _operand(0x4000000, F32, shape, (4, 16384), out=True)]
+    arr = (_lib.Operand * 2)(*ops)
+    assert _lib.lib.b200_ew_plan_ex(2, arr, 0, ctypes.byref(free)) == 0
+    assert free.variant == _lib.EW_TILED_REG and free.staged_mask == 0b01
+    assert tuple(free.shape[:2]) == (2048, 4096)
+    # permuted 3-D: (2, 0, 1) transpose of a C array, same permutation on both sides -> flat again
+    shape3, st3 = (64, 16, 32), (4, 8192, 256)
+    ops = [_operand(0x1000, F32, shape3, st3), _operand(0x800000, F32, shape3, st3, out=True)]
+    arr = (_lib.Operand * 2)(*ops)
+    assert _lib.lib.b200_ew_plan_ex(2, arr, 0, ctypes.byref(free)) == 0
+    assert free.variant == _lib.EW_FLAT and free.ndim == 1

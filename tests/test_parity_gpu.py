@@ -546,3 +546,26 @@ def test_reduction_kernel_several_arrays_one_layout(cp, shape, axis):
 def _mm_preamble(cp):
     from cupy_b200._core import _routines_statistics
     return _routines_statistics._min_max_preamble
+
+
+def test_f_ordered_and_permuted_operands_free_loop_order(cp):
+    """The planner may reorder loop dims unless the kernel can observe the linear index `i`."""
+    a = rnd((300, 500), 'float32')
+    d = cp.asarray(a)
+    f = d.T                                        # F-ordered view
+    r = f.astype(np.float16)
+    assert r.strides == (2, 1000)                  # order='K' keeps the layout
+    np.testing.assert_array_equal(r.get(), a.T.astype(np.float16))
+    np.testing.assert_array_equal((f * 2 + f).get(), a.T * 2 + a.T)
+    out_f = cp.empty((500, 300), np.float32).T     # C-ordered inputs into an F-ordered output
+    cp.add(d, d, out=out_f)
+    np.testing.assert_array_equal(out_f.get(), a + a)
+    p = cp.asarray(rnd((8, 9, 10), 'int32')).transpose(2, 0, 1)
+    np.testing.assert_array_equal((p + p).get(), p.get() * 2)
+    # a kernel that reads `i` keeps C order: i is the C-order linear index of the logical shape
+    k = cp.ElementwiseKernel('T x', 'int64 y', 'y = i', 'lin_index_forder')
+    got = k(f).get()
+    np.testing.assert_array_equal(got, np.arange(a.size, dtype=np.int64).reshape(500, 300))
+    kr = cp.ElementwiseKernel('raw T x, int64 n', 'T y', 'y = x[n - 1 - i]', 'reverse_raw')
+    flat = cp.asarray(a.reshape(-1))
+    np.testing.assert_array_equal(kr(flat, a.size, cp.empty((a.size,), np.float32)).get(), a.reshape(-1)[::-1])
