@@ -70,6 +70,44 @@ class NCCLBackend:
     def recv(self, out_array, peer, stream=None):
         dist.recv(self._tensor(out_array), src=peer)
 
+    def send_recv(self, in_array, out_array, peer, stream=None):
+        """Grouped send + receive with one peer (cupyx/distributed/_nccl_comm.py:385-395)."""
+        ops = [dist.P2POp(dist.isend, self._tensor(in_array), peer),
+               dist.P2POp(dist.irecv, self._tensor(out_array), peer)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def _check_first_dim(self, name, which, array):
+        if array.shape[0] != self._n_devices:
+            raise RuntimeError('%s requires %s to have %d elements in its first dimension, found %s'
+                               % (name, which, self._n_devices, tuple(array.shape)))
+
+    def scatter(self, in_array, out_array, root=0, stream=None):
+        """`in_array` has shape (total_ranks, ...) on the root (:397-414)."""
+        self._check_first_dim('scatter', 'in_array', in_array)
+        dst = self._tensor(out_array)
+        chunks = None
+        if self.rank == root:
+            chunks = list(self._tensor(in_array).reshape(self._n_devices, -1).unbind(0))
+            chunks = [c.reshape(dst.shape) for c in chunks]
+        dist.scatter(dst, chunks, src=root)
+
+    def gather(self, in_array, out_array, root=0, stream=None):
+        """`out_array` has shape (total_ranks, ...) (:416-434)."""
+        self._check_first_dim('gather', 'out_array', out_array)
+        src = self._tensor(in_array)
+        outs = None
+        if self.rank == root:
+            flat = self._tensor(out_array).reshape(self._n_devices, -1)
+            outs = [flat[i].reshape(src.shape) for i in range(self._n_devices)]
+        dist.gather(src, outs, dst=root)
+
+    def all_to_all(self, in_array, out_array, stream=None):
+        """Row i of `in_array` goes to rank i; row i of `out_array` comes from rank i (:436-456)."""
+        self._check_first_dim('all_to_all', 'in_array', in_array)
+        self._check_first_dim('all_to_all', 'out_array', out_array)
+        dist.all_to_all_single(self._tensor(out_array), self._tensor(in_array))
+
     def barrier(self):
         dist.barrier()
 

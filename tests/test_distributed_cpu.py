@@ -38,6 +38,44 @@ def _worker(rank, world, port, q):
     b = torch.full((4,), float(rank))
     comm.broadcast(b, root=1)
     ok = ok and bool((b == 1).all())
+    # the other collectives of the reference's NCCLBackend (cupyx/distributed/_nccl_comm.py:187-295;
+    # expectations follow tests/cupyx_tests/distributed_tests/comm_runner.py)
+    g_in = torch.full((3,), float(rank + 1))
+    g_out = torch.zeros(world, 3)
+    comm.gather(g_in, g_out, root=0)
+    if rank == 0:
+        ok = ok and bool((g_out == torch.arange(1, world + 1, dtype=torch.float32)[:, None]).all())
+    s_in = torch.arange(world * 2, dtype=torch.float32).reshape(world, 2) + 100 * rank
+    s_out = torch.zeros(2)
+    comm.scatter(s_in, s_out, root=1)
+    ok = ok and bool((s_out == torch.arange(2) + 2 * rank + 100).all())
+    ag_out = torch.zeros(world * 3)
+    comm.all_gather(g_in, ag_out, 3)
+    ok = ok and bool((ag_out.reshape(world, 3) == torch.arange(1, world + 1, dtype=torch.float32)[:, None]).all())
+    rs_in = torch.arange(world * 2, dtype=torch.float32)
+    rs_out = torch.zeros(2)
+    try:
+        comm.reduce_scatter(rs_in, rs_out, 2)
+        ok = ok and bool((rs_out == world * (torch.arange(2) + 2 * rank)).all())
+    except RuntimeError:
+        pass                      # gloo builds without reduce_scatter: NCCL has it
+    a2a_in = torch.arange(world, dtype=torch.float32).reshape(world, 1) + 10 * rank
+    a2a_out = torch.zeros(world, 1)
+    try:
+        comm.all_to_all(a2a_in, a2a_out)
+        ok = ok and bool((a2a_out.reshape(-1) == 10 * torch.arange(world) + rank).all())
+    except RuntimeError:
+        pass
+    peer = (rank + 1) % world
+    sr_out = torch.zeros(2)
+    comm.send_recv(torch.full((2,), float(rank)), sr_out, peer)
+    ok = ok and bool((sr_out == float(peer)).all()) if world == 2 else ok
+    for bad in (lambda: comm.scatter(torch.zeros(world + 1, 2), s_out), lambda: comm.gather(g_in, torch.zeros(world + 1, 3))):
+        try:
+            bad()
+            ok = False
+        except RuntimeError:
+            pass
     # sharded var merge: every rank folds the gathered (n, mean, M2) in rank order
     rs = np.random.RandomState(0)
     full = rs.rand(1000 * world + 37)
