@@ -199,8 +199,7 @@ def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_ma
         vec = vec if vec == full_vec else 1
         n = layout.n_reduce
         # == rows_group() in csrc/reduce_impl.cuh: the largest group whose unrolled batch fits the row
-        group = (_THREADS if n >= 2048 else 32 if n >= 32 * vec * unroll else 8 if n >= 8 * vec * unroll
-                 else 1 if (n >= vec * unroll and vec > 1) else 32 if n >= 32 else 8 if n >= 8 else 1)
+        group = _THREADS if n >= 2048 else 32 if n >= 32 * vec * unroll else 8 if n >= 8 * vec else 1
         rpb = _THREADS // group
         g = max(1, min((layout.n_out + rpb - 1) // rpb, sm * 64))
         grid = (g, 1, 1)

@@ -211,6 +211,17 @@ __device__ __forceinline__ void reduce_rows_body(
                 ta.fold(v, static_cast<index_t>(base + int64_t(g) * VEC), static_cast<index_t>(GROUP * VEC),
                         static_cast<index_t>(1));
             }
+            // whole vectors that do not fill an unrolled batch: one 16-byte load per lane and step
+            // (rows shorter than GROUP * VEC * UNROLL live here entirely)
+            if (VEC > 1) {
+                for (; base + int64_t(GROUP) * VEC <= n; base += int64_t(GROUP) * VEC) {
+                    Pack<typename Op::in_t, VEC> v1;
+                    load_pack(v1, xr + base + int64_t(g) * VEC);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k)
+                        ta.fold_one_lane(k, v1[k], static_cast<index_t>(base + int64_t(g) * VEC + k));
+                }
+            }
             for (int64_t i = base + g; i < n; i += GROUP) ta.fold_one(xr[i], static_cast<index_t>(i));
         }
         acc_t r = ta.result();

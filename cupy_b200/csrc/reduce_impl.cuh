@@ -68,14 +68,9 @@ static int full_grid(int64_t n, int vec, int unroll, int sm) {
 // so that the row is read with full vector batches and not through the scalar tail loop
 static int rows_group(int64_t n, int vec, int unroll) {
     if (n >= 2048) return kRedThreads;
-    if (n >= int64_t(32) * vec * unroll) return 32;
-    if (n >= int64_t(8) * vec * unroll) return 8;
-    // shorter rows: a thread per row when the row holds at least one vector batch (16-byte loads,
-    // the lines are completed from L1 by the thread's next loads); else the coalesced scalar tail loop
-    if (n >= int64_t(vec) * unroll && vec > 1) return 1;
-    if (n >= 32) return 32;
-    if (n >= 8) return 8;
-    return 1;
+    if (n >= int64_t(32) * vec * unroll) return 32;     // unrolled batches of a warp
+    if (n >= int64_t(8) * vec) return 8;                // unrolled batches or single-vector steps of 8 lanes
+    return 1;                                           // a thread per row
 }
 
 static void cols_geometry(int64_t batch, int64_t n, int64_t cols, int vec, int sm, Geometry* g) {
