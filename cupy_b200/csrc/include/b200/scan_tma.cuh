@@ -159,9 +159,13 @@ __device__ __forceinline__ void scan_tma_body(const void* tm_in, const void* tm_
         const int count = (it >= LAG && DBG == 0) ? int((tiles - wave0) < G ? (tiles - wave0) : G) : 0;
 #pragma unroll
         for (int r = 0; r < kMaxGather; ++r) {
-            const int bp = tid + r * THREADS;
             pf_status[r] = 1u;
             pf_bits[r] = to_bits(Op::template identity<T>());
+        }
+#pragma unroll
+        for (int r = 0; r < kMaxGather; ++r) {
+            if (r * THREADS >= count) break;          // block-uniform: G <= THREADS needs one round only
+            const int bp = tid + r * THREADS;
             if (bp < count) pf_status[r] = Slot::peek(slots + wave0 + bp, pf_bits[r]);
         }
         // ================= phase A: local scan of my tile `it` =================
@@ -179,12 +183,23 @@ __device__ __forceinline__ void scan_tma_body(const void* tm_in, const void* tm_
 #pragma unroll
                 for (int k = 0; k < EPC; ++k) item[c * EPC + k] = v[k];
             }
-            // the ragged last row lies outside the tensor map (TMA zero-filled it): read it directly
-            if (row == full_rows && full_rows != rows) {
+            // the ragged last row lies outside the tensor map (TMA zero-filled it): one thread of the
+            // whole grid reads it directly -- through its stage, so the hot path carries no predicates
+            if (__builtin_expect(row == full_rows && full_rows != rows, 0)) {
                 const int cnt = int(n - full_rows * ITEMS);
+                T* srow = reinterpret_cast<T*>(st_a);
+#pragma unroll 1
+                for (int j = 0; j < ITEMS; ++j) {
+                    const uint32_t off = swz128(tid, j / EPC) + (j % EPC) * sizeof(T);
+                    *reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(srow) + off) =
+                        (j < cnt) ? x[row * ITEMS + j] : Op::template identity<T>();
+                }
 #pragma unroll
-                for (int j = 0; j < ITEMS; ++j)
-                    item[j] = (j < cnt) ? x[row * ITEMS + j] : Op::template identity<T>();
+                for (int c = 0; c < 8; ++c) {
+                    const Pack<T, EPC> v = *reinterpret_cast<const Pack<T, EPC>*>(st_a + swz128(tid, c));
+#pragma unroll
+                    for (int k = 0; k < EPC; ++k) item[c * EPC + k] = v[k];
+                }
             }
 #pragma unroll
             for (int j = 1; j < ITEMS; ++j) item[j] = Op::combine(item[j - 1], item[j]);
@@ -204,6 +219,7 @@ __device__ __forceinline__ void scan_tma_body(const void* tm_in, const void* tm_
             T before = Op::template identity<T>(), all = Op::template identity<T>();
 #pragma unroll
             for (int r = 0; r < kMaxGather; ++r) {
+                if (r * THREADS >= count) break;
                 const int bp = tid + r * THREADS;
                 if (bp < count) {
                     while (pf_status[r] == 0u) pf_status[r] = Slot::peek(slots + wave0 + bp, pf_bits[r]);
@@ -259,7 +275,6 @@ __device__ __forceinline__ void scan_tma_body(const void* tm_in, const void* tm_
             }
             if (DBG != 2) {
                 const int64_t row = tile * THREADS + tid;
-                const bool ragged = (row == full_rows) && (full_rows != rows);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     Pack<T, EPC>* p = reinterpret_cast<Pack<T, EPC>*>(st + swz128(tid, c));
@@ -267,11 +282,14 @@ __device__ __forceinline__ void scan_tma_body(const void* tm_in, const void* tm_
 #pragma unroll
                     for (int e = 0; e < EPC; ++e) v[e] = Op::combine(prefix, v[e]);
                     *p = v;
-                    if (ragged) {
-                        const int cnt = int(n - full_rows * ITEMS);
-#pragma unroll
-                        for (int e = 0; e < EPC; ++e)
-                            if (c * EPC + e < cnt) y[row * ITEMS + c * EPC + e] = v[e];
+                }
+                // the ragged last row is clipped by the TMA store: its owner writes it directly
+                if (__builtin_expect((row == full_rows) && (full_rows != rows), 0)) {
+                    const int cnt = int(n - full_rows * ITEMS);
+#pragma unroll 1
+                    for (int j = 0; j < cnt; ++j) {
+                        const uint32_t off = swz128(tid, j / EPC) + (j % EPC) * sizeof(T);
+                        y[row * ITEMS + j] = *reinterpret_cast<const T*>(st + off);
                     }
                 }
             }

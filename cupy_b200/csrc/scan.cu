@@ -76,8 +76,12 @@ static int run_tma(int op, const void* x, void* y, int64_t n, void* wsp, size_t 
     constexpr int ITEMS = 128 / int(sizeof(T));
     if (n < kScanTmaMinN || n / ITEMS >= (int64_t(1) << 31)) return B200_E_UNSUPPORTED;
     if (ws_bytes < scan_tma_ws_bytes(n)) return B200_E_UNSUPPORTED;
-    static int cfg = [] { const char* e = getenv("B200_SCAN_CFG"); return e ? atoi(e) : 0; }();
+    static const int cfg_env = [] { const char* e = getenv("B200_SCAN_CFG"); return e ? atoi(e) : 0; }();
+    int cfg = cfg_env;
     if (cfg < 0) return B200_E_UNSUPPORTED;
+    // default by item size (B200 sweep, profiles/r01_scan_probe_s7.log): 4-byte items run best as two
+    // 128-row blocks per SM (f32 2^28: 5683 vs 5364 GB/s), 8-byte items as one 256-row block
+    if (cfg == 0) cfg = sizeof(T) == 4 ? 163 : 263;
     DeviceInfo di;
     int st = device_info(&di);
     if (st) return st;
@@ -97,7 +101,6 @@ static int run_tma(int op, const void* x, void* y, int64_t n, void* wsp, size_t 
         if (op == B200_OP_CUMSUM) return launch_tma<T, ScanSum, TH, ST, LG>(tin, tout, xi, yo, n, wsp, di.sm_count, stream); \
         return launch_tma<T, ScanProd, TH, ST, LG>(tin, tout, xi, yo, n, wsp, di.sm_count, stream);         \
     }
-    B200_TMA_CASE(0, 256, 6, 3)
     B200_TMA_CASE(162, 128, 6, 2)
     B200_TMA_CASE(163, 128, 6, 3)
     B200_TMA_CASE(252, 256, 5, 2)
