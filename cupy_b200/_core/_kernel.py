@@ -348,6 +348,8 @@ def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stre
         threads, unroll, vec = 288, tunables['tma_stages'], plan.vec   # "unroll" slot = ring depth override (0 = auto)
     elif variant == _lib.EW_FLAT:
         unroll, vec = tunables['flat_unroll'], plan.vec
+        if plan.staged_mask:          # periodic operands: the plan assumed 256-thread blocks
+            threads = 256
     else:
         unroll, vec = tunables['row_unroll'], plan.vec
     arginfo = tuple(

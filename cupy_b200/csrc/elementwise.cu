@@ -79,6 +79,7 @@ extern "C" __attribute__((visibility("default"))) int b200_ufunc_launch(int ufun
     switch (plan->variant) {
         case B200_EW_FLAT:
             if (plan->vec >= k->vec) { fn = k->flat_v; eff.vec = k->vec; }
+            else if (plan->staged_mask) return fail(B200_E_UNSUPPORTED, "periodic FLAT plan needs the full-vector kernel");
             else { fn = k->flat_1; eff.vec = 1; }
             unroll = k->unroll_flat;
             break;

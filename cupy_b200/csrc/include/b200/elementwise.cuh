@@ -74,9 +74,15 @@ struct FlatTiler {
     int64_t base;
     bool full;
 
+    int poff;     // periodic operands: this thread's element offset inside the period (same for every tile and u)
+
     B200_DEVICE explicit FlatTiler(const EwParams& p_) : p(p_) {
         base = int64_t(blockIdx.x) * kTile;
         full = base + kTile <= p.size;
+        // FLAT with periodic operands (p.staged_mask, period p.tile_axis elements): a row vector
+        // broadcast over a dense array.  The host guarantees THREADS * VEC % period == 0, so the
+        // element (base + (u * THREADS + tid) * VEC) % period does not depend on the tile or on u.
+        poff = p.staged_mask ? int((int64_t(threadIdx.x) * VEC) % p.tile_axis) : 0;
     }
     B200_DEVICE bool valid() const { return base < p.size; }
     B200_DEVICE void next() {
@@ -93,6 +99,14 @@ struct FlatTiler {
     template <bool FULL, class T>
     B200_DEVICE void load(int a, Pack<T, VEC> (&r)[UNROLL]) const {
         const T* __restrict__ ptr = reinterpret_cast<const T*>(p.arg[a].ptr);
+        if ((p.staged_mask >> a) & 1u) {
+            // periodic operand: one vector serves every unroll step (period % VEC == 0: never straddles)
+            Pack<T, VEC> v;
+            load_pack(v, ptr + poff);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) r[u] = v;
+            return;
+        }
         if (FULL) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) load_pack(r[u], ptr + index(u, 0));

@@ -341,6 +341,32 @@ static int plan_impl(int nargs, const b200_operand_t* args, uint32_t flags, b200
         if (is_array(args[a]) && st[a][0] != dtype_size(args[a].dtype)) flat = false;
 
     int vec = std::max(1, 16 / max_item);
+    // ---- FLAT with periodic operands: a dense (rows, inner) loop whose other operands are row vectors
+    //      broadcast over the rows (stride 0, unit stride).  The dense operands are walked as 1-D; a
+    //      periodic operand is indexed by (i % inner), which is constant per thread when 256 * vec is a
+    //      multiple of inner (FlatTiler).  Requires full vector alignment everywhere.
+    if (nd == 2) {
+        uint32_t pmask = 0;
+        bool ok = shape[1] % vec == 0 && (int64_t(256) * vec) % shape[1] == 0;
+        for (int a = 0; a < nargs && ok; ++a) {
+            if (!is_array(args[a])) continue;
+            const int isz = dtype_size(args[a].dtype);
+            if (reinterpret_cast<uintptr_t>(args[a].data) % (uintptr_t(vec) * isz)) ok = false;
+            if (st[a][1] != isz) { ok = false; break; }
+            if (st[a][0] == 0 && !args[a].is_output) pmask |= 1u << a;
+            else if (st[a][0] != shape[1] * isz) ok = false;
+        }
+        if (ok && pmask) {
+            plan->variant = B200_EW_FLAT;
+            plan->ndim = 1;
+            plan->shape[0] = size;
+            for (int a = 0; a < nargs; ++a) plan->strides[a][0] = is_array(args[a]) ? dtype_size(args[a].dtype) : 0;
+            plan->vec = vec;
+            plan->staged_mask = pmask;
+            plan->tile_axis = int32_t(shape[1]);
+            return 0;
+        }
+    }
     if (flat) {
         plan->variant = B200_EW_FLAT;
         for (; vec > 1; vec >>= 1) {

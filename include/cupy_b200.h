@@ -129,9 +129,11 @@ typedef struct b200_ew_plan {
     int32_t  ndim;                     /* collapsed rank */
     int32_t  vec;                      /* elements per vector access (1,2,4,8,16) */
     int32_t  idx32;                    /* 1 if every offset fits in int32 */
-    int32_t  tile_axis;                /* TILED: collapsed dim along which staged operands are unit-stride */
+    int32_t  tile_axis;                /* TILED*: collapsed dim along which staged operands are unit-stride;
+                                          FLAT with periodic operands: the period in elements */
     int32_t  nargs;
-    uint32_t staged_mask;              /* TILED: bit k set = operand k is staged through shared memory */
+    uint32_t staged_mask;              /* TILED*: bit k set = operand k is staged (unit-stride along tile_axis);
+                                          FLAT: bit k set = operand k is a row vector broadcast over the rows (periodic) */
     uint32_t reserved;
     int64_t  size;                     /* number of loop elements */
     int64_t  shape[B200_MAX_NDIM];

@@ -77,13 +77,24 @@ def test_plan_misaligned_pointer_drops_vector_width():
     assert p.vec == 2
 
 
-def test_plan_row_broadcast_is_rowwise_vectorised():
-    # x[1024,256] + v[256]: v has stride 0 along dim 0
+def test_plan_row_broadcast_is_flat_with_a_periodic_operand():
+    # x[1024,256] + v[256]: v has stride 0 along dim 0 and its length divides 256 * vec -> the dense
+    # operands are walked 1-D and v is indexed by (i % 256), constant per thread (FlatTiler)
     s, p = _plan([_operand(0x10000, F32, (1024, 256), (1024, 4)), _operand(0x90000, F32, (1024, 256), (0, 4)),
                   _operand(0xa0000, F32, (1024, 256), (1024, 4), out=True)])
     assert s == 0
+    assert (p.variant, p.ndim, p.vec, p.size) == (_lib.EW_FLAT, 1, 4, 1024 * 256)
+    assert p.staged_mask == 0b010 and p.tile_axis == 256
+    # a row length that does not divide 1024 elements stays ROWWISE (vectors along the row)
+    s, p = _plan([_operand(0x10000, F32, (1024, 768), (3072, 4)), _operand(0x90000, F32, (1024, 768), (0, 4)),
+                  _operand(0xa00000, F32, (1024, 768), (3072, 4), out=True)])
+    assert s == 0
     assert (p.variant, p.ndim, p.vec) == (_lib.EW_ROWWISE, 2, 4)
-    assert list(p.shape[:2]) == [1024, 256]
+    assert list(p.shape[:2]) == [1024, 768]
+    # a padded (non-dense) left operand too
+    s, p = _plan([_operand(0x10000, F32, (1024, 256), (2048, 4)), _operand(0x90000, F32, (1024, 256), (0, 4)),
+                  _operand(0xa00000, F32, (1024, 256), (1024, 4), out=True)])
+    assert s == 0 and p.variant == _lib.EW_ROWWISE
 
 
 def test_plan_column_broadcast():

@@ -193,7 +193,8 @@ def test_classification_of_config_shapes(dry):
     cp.exp(xt)
     assert dry[-1]['variant'] == _lib.EW_TILED_REG and dry[-1]['tile_axis'] == 0 and dry[-1]['staged_mask'] == 1
     cp.add(cp.empty((256, 128, 64), 'f'), v)
-    assert dry[-1]['variant'] == _lib.EW_ROWWISE and dry[-1]['vec'] == 4 and dry[-1]['ndim'] == 2
+    # a row vector over a dense array: 1-D walk, the vector is a periodic operand (period 64 | 1024)
+    assert dry[-1]['variant'] == _lib.EW_FLAT and dry[-1]['vec'] == 4 and dry[-1]['ndim'] == 1 and dry[-1]['staged_mask'] == 2
     cp.ElementwiseKernel('T x, T v', 'T z', 'z = exp(x) + v', 'fused')(xt, v)
     assert dry[-1]['variant'] == _lib.EW_TILED_REG and 'RegTileTiler<3, 4, 1, 177ull>' in dry[-1]['source']
     h = cp.empty((n,), 'e')

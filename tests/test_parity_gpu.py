@@ -569,3 +569,34 @@ def test_f_ordered_and_permuted_operands_free_loop_order(cp):
     kr = cp.ElementwiseKernel('raw T x, int64 n', 'T y', 'y = x[n - 1 - i]', 'reverse_raw')
     flat = cp.asarray(a.reshape(-1))
     np.testing.assert_array_equal(kr(flat, a.size, cp.empty((a.size,), np.float32)).get(), a.reshape(-1)[::-1])
+
+
+@pytest.mark.parametrize('dt', ['float32', 'float16', 'float64', 'int32', 'int8'])
+@pytest.mark.parametrize('shape', [(1000, 256), (7, 5, 64), (513, 1024), (300, 8), (64, 4), (1000, 768), (33, 100)])
+def test_row_vector_broadcast_periodic_flat(cp, shape, dt):
+    """Bias-add pattern: a row vector broadcast over a dense array.  Row lengths that divide
+    256 * vec run on the FLAT tiler with a periodic operand; the rest on the ROWWISE tiler."""
+    a = rnd(shape, dt)
+    v = rnd((shape[-1],), dt)
+    d, dv = cp.asarray(a), cp.asarray(v)
+    np.testing.assert_array_equal((d + dv).get(), a + v)
+    np.testing.assert_array_equal((dv * d).get(), v * a)
+    out = cp.empty(shape, dt)
+    cp.subtract(dv, d, out=out)
+    np.testing.assert_array_equal(out.get(), v - a)
+    np.testing.assert_array_equal(cp.maximum(d, dv).get(), np.maximum(a, v))
+    k = cp.ElementwiseKernel('T x, T v', 'T z, int64 idx', 'z = x + v; idx = i', 'bias_and_index')
+    z, idx = k(d, dv)
+    np.testing.assert_array_equal(z.get(), a + v)
+    np.testing.assert_array_equal(idx.get(), np.arange(a.size).reshape(shape))
+    # in place and with two periodic operands
+    d2 = cp.asarray(a.copy())
+    d2 += dv
+    np.testing.assert_array_equal(d2.get(), a + v)
+    k3 = cp.ElementwiseKernel('T x, T v, T w', 'T z', 'z = x + v - w', 'shift2')
+    # float16 operands are promoted to float inside a kernel expression (one rounding at the store)
+    want3 = (a.astype(np.float32) + v - v).astype(dt) if dt == 'float16' else a + v - v
+    np.testing.assert_array_equal(k3(d, dv, dv, block_size=128).get(), want3)
+    # misaligned views leave the periodic path
+    if shape[-1] >= 8:
+        np.testing.assert_array_equal((d[..., 1:] + dv[1:]).get(), a[..., 1:] + v[1:])
