@@ -213,16 +213,18 @@ def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_ma
         vec = _pick_vec([a.ptr for a in xs], layout.n_out, [a.dtype.itemsize for a in xs], cv)
         vec = vec if vec == cv else 1
         ru = 2 if vec >= 8 else 4
-        tiles = (layout.n_out + 32 * vec - 1) // (32 * vec)
+        wc = 8 if layout.n_out >= 8 * 32 * vec * 2 else 1      # == cols_wc() in csrc/reduce_impl.cuh (plain functors)
+        block_cols = 32 * vec * wc
+        tiles = (layout.n_out + block_cols - 1) // block_cols
         want = (sm * 8 + tiles * layout.batch - 1) // (tiles * layout.batch)
         nsplit = max(1, min(want, layout.n_reduce // 64, 65535))
         grid = (tiles, nsplit, layout.batch)
         a0, a1 = layout.n_reduce, layout.n_out
         if nsplit > 1:
             ws_need = _TICKET_BYTES + layout.batch * nsplit * layout.n_out * acc_bytes
-        body = ('b200::reduce_cols_body<_Op, %d, %d>(p.op, p.x, p.y, p.a0, p.a1, '
-                'reinterpret_cast<_Op::acc_t*>(p.ws0), reinterpret_cast<uint32_t*>(p.ws1));' % (vec, ru))
-        tag = 'cols_v%d' % vec
+        body = ('b200::reduce_cols_body<_Op, %d, %d, %d>(p.op, p.x, p.y, p.a0, p.a1, '
+                'reinterpret_cast<_Op::acc_t*>(p.ws0), reinterpret_cast<uint32_t*>(p.ws1));' % (vec, ru, wc))
+        tag = 'cols_v%d_w%d' % (vec, wc)
 
     key = ('s', tag, index64, tuple(a.dtype.char for a in xs), out.dtype.char, type_map, reduce_type,
            tuple(a.descr.char for a in in_args if isinstance(a, CScalar)))

@@ -245,22 +245,31 @@ __device__ __forceinline__ void reduce_rows_body(
 // (atomic ticket) folds them in row order.
 // workspace: batch*nsplit*cols partials, then batch*gridDim.x zeroed tickets.
 // ---------------------------------------------------------------------------
-template <class Op, int VEC, int RU>
+// WC = warps standing side by side across the columns (1 or 8); the other 8 / WC warp rows split the
+// reduced rows and meet in shared memory.  WC = 8 makes a block read 8 * 32 * VEC contiguous elements
+// of every row (4 KB for float32: whole DRAM pages instead of 512-byte strips): 94 % -> 109 % of the
+// copy peak on sum / max over axis 0 of a 32768^2 float32 array (WC = 4, 2 KB per visit: no gain).
+// Functors with their own lane state (arg-reductions, moments) keep WC = 1: fewer column tiles mean more
+// row splits, and their split partials are expensive to merge (measured 2x slower at WC = 8).
+template <class Op, int VEC, int RU, int WC = 1>
 __device__ __forceinline__ void reduce_cols_body(
         const Op& op, typename in_ptr<Op>::type x, typename Op::out_t* __restrict__ y,
         int64_t n, int64_t cols, typename Op::acc_t* partials, uint32_t* tickets) {
     typedef typename Op::acc_t acc_t;
     typedef typename Op::index_t index_t;
     constexpr int kWarps = 8;
+    constexpr int kWarpRows = kWarps / WC;            // warps sharing a column strip
     constexpr int kTileCols = 32 * VEC;
+    constexpr int kBlockCols = WC * kTileCols;
     __shared__ __align__(16) char smem_raw[kWarps * kTileCols * sizeof(acc_t)];
-    acc_t (*smem)[kTileCols] = reinterpret_cast<acc_t (*)[kTileCols]>(smem_raw);
+    acc_t (*smem)[kBlockCols] = reinterpret_cast<acc_t (*)[kBlockCols]>(smem_raw);
     __shared__ bool is_last;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wc = warp % WC, wr = warp / WC;
     const int64_t b = blockIdx.z;
     const int nsplit = gridDim.y, split = blockIdx.y;
-    const int64_t c0 = (int64_t(blockIdx.x) * 32 + lane) * VEC;
+    const int64_t c0 = ((int64_t(blockIdx.x) * WC + wc) * 32 + lane) * VEC;
     const bool col_ok = c0 < cols;     // VEC > 1 => cols % VEC == 0 => whole pack in range
     const int64_t rows_per_split = (n + nsplit - 1) / nsplit;
     const int64_t r_begin = int64_t(split) * rows_per_split;
@@ -269,14 +278,14 @@ __device__ __forceinline__ void reduce_cols_body(
 
     ThreadAcc<Op, RU, VEC> ta(op);
     if (col_ok) {
-        int64_t r = r_begin + warp;
-        for (; r + int64_t(RU - 1) * kWarps < r_end; r += int64_t(RU) * kWarps) {
+        int64_t r = r_begin + wr;
+        for (; r + int64_t(RU - 1) * kWarpRows < r_end; r += int64_t(RU) * kWarpRows) {
             Pack<typename Op::in_t, VEC> v[RU];
 #pragma unroll
-            for (int u = 0; u < RU; ++u) load_pack(v[u], xb + (r + int64_t(u) * kWarps) * cols);
-            ta.fold(v, static_cast<index_t>(r), static_cast<index_t>(kWarps), static_cast<index_t>(0));
+            for (int u = 0; u < RU; ++u) load_pack(v[u], xb + (r + int64_t(u) * kWarpRows) * cols);
+            ta.fold(v, static_cast<index_t>(r), static_cast<index_t>(kWarpRows), static_cast<index_t>(0));
         }
-        for (; r < r_end; r += kWarps) {
+        for (; r < r_end; r += kWarpRows) {
             Pack<typename Op::in_t, VEC> v;
             load_pack(v, xb + r * cols);
 #pragma unroll
@@ -284,15 +293,15 @@ __device__ __forceinline__ void reduce_cols_body(
         }
     }
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) smem[warp][lane * VEC + k] = ta.result_lane(k);
+    for (int k = 0; k < VEC; ++k) smem[wr][(wc * 32 + lane) * VEC + k] = ta.result_lane(k);
     __syncthreads();
 
-    const int64_t tile_c0 = int64_t(blockIdx.x) * kTileCols;
-    for (int t = threadIdx.x; t < kTileCols; t += blockDim.x) {
+    const int64_t tile_c0 = int64_t(blockIdx.x) * kBlockCols;
+    for (int t = threadIdx.x; t < kBlockCols; t += blockDim.x) {
         if (tile_c0 + t >= cols) continue;
         acc_t a = smem[0][t];
 #pragma unroll
-        for (int w = 1; w < kWarps; ++w) a = op.combine(a, smem[w][t]);
+        for (int w = 1; w < kWarpRows; ++w) a = op.combine(a, smem[w][t]);
         if (nsplit == 1) y[b * cols + tile_c0 + t] = op.post(a, n);
         else partials[(b * nsplit + split) * cols + tile_c0 + t] = a;
     }
@@ -307,7 +316,7 @@ __device__ __forceinline__ void reduce_cols_body(
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int t = threadIdx.x; t < kTileCols; t += blockDim.x) {
+    for (int t = threadIdx.x; t < kBlockCols; t += blockDim.x) {
         if (tile_c0 + t >= cols) continue;
         acc_t a = load_volatile(partials + (b * nsplit) * cols + tile_c0 + t);
         for (int s = 1; s < nsplit; ++s)

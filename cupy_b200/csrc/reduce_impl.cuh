@@ -32,11 +32,11 @@ __global__ void __launch_bounds__(kRedThreads) reduce_rows_kernel(
     reduce_rows_body<Op, VEC, UNROLL, kRedThreads, GROUP>(op, x, y, rows, n);
 }
 
-template <class Op, int VEC, int RU>
+template <class Op, int VEC, int RU, int WC>
 __global__ void __launch_bounds__(kRedThreads) reduce_cols_kernel(
         Op op, const typename Op::in_t* x, typename Op::out_t* y, int64_t n, int64_t cols,
         typename Op::acc_t* partials, uint32_t* tickets) {
-    reduce_cols_body<Op, VEC, RU>(op, x, y, n, cols, partials, tickets);
+    reduce_cols_body<Op, VEC, RU, WC>(op, x, y, n, cols, partials, tickets);
 }
 
 // ---- geometry ---------------------------------------------------------------
@@ -73,8 +73,14 @@ static int rows_group(int64_t n, int vec, int unroll) {
     return 1;                                           // a thread per row
 }
 
-static void cols_geometry(int64_t batch, int64_t n, int64_t cols, int vec, int sm, Geometry* g) {
-    const int64_t tiles = (cols + 32 * vec - 1) / (32 * vec);
+// wide matrices and plain functors: the 8 warps of a block stand side by side across the columns
+// (reduce_cols_body<WC = 8>, 4 KB of every row per visit; WC = 4 measured no gain); functors with
+// their own lane state keep one strip per block
+static int cols_wc(int64_t cols, int vec, bool heavy) { return (!heavy && cols >= int64_t(8) * 32 * vec * 2) ? 8 : 1; }
+
+static void cols_geometry(int64_t batch, int64_t n, int64_t cols, int vec, int sm, bool heavy, Geometry* g) {
+    const int64_t block_cols = int64_t(32) * vec * cols_wc(cols, vec, heavy);
+    const int64_t tiles = (cols + block_cols - 1) / block_cols;
     // enough blocks for ~8 per SM, at least 64 rows per split
     int64_t want = (int64_t(sm) * 8 + tiles * batch - 1) / (tiles * batch);
     int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>(want, n / 64));
@@ -148,16 +154,16 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
         Geometry g = {};
         if (query) {
             // worst case over vector widths (tickets live in the fixed header)
-            cols_geometry(d->batch, d->n_reduce, d->n_out, 1, 296, &g);
+            cols_geometry(d->batch, d->n_reduce, d->n_out, 1, 296, fast_lanes<Op>::value, &g);
             Geometry g2 = {};
-            cols_geometry(d->batch, d->n_reduce, d->n_out, CV, 296, &g2);
+            cols_geometry(d->batch, d->n_reduce, d->n_out, CV, 296, fast_lanes<Op>::value, &g2);
             const size_t pc = std::max(g.partial_count, g2.partial_count);
             *need = pc ? kTicketBytes + align_up(pc * sizeof(acc_t), 16) : 0;
             return 0;
         }
         int vec = pick_vec<CV>(x, d->n_out, sizeof(in_t));
         if (vec != CV) vec = 1;
-        cols_geometry(d->batch, d->n_reduce, d->n_out, vec, di.sm_count, &g);
+        cols_geometry(d->batch, d->n_reduce, d->n_out, vec, di.sm_count, fast_lanes<Op>::value, &g);
         if (g.ticket_count * sizeof(uint32_t) > kTicketBytes) {   // cannot happen: splits only when tiles*batch < 8*SMs
             g.gy = 1; g.partial_count = 0; g.ticket_count = 0;
         }
@@ -167,10 +173,11 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
         uint32_t* tickets = static_cast<uint32_t*>(ws);
         acc_t* partials = reinterpret_cast<acc_t*>(static_cast<char*>(ws) + kTicketBytes);
         const dim3 grid(g.gx, g.gy, g.gz);
-        if (vec == CV)
-            reduce_cols_kernel<Op, CV, CU><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, d->n_out, partials, tickets);
-        else
-            reduce_cols_kernel<Op, 1, 4><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, d->n_out, partials, tickets);
+        const int wc = cols_wc(d->n_out, vec, fast_lanes<Op>::value);
+#define B200_COLS(V, R, W) reduce_cols_kernel<Op, V, R, W><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, d->n_out, partials, tickets)
+        if (vec == CV) { if (wc == 8) B200_COLS(CV, CU, 8); else B200_COLS(CV, CU, 1); }
+        else { if (wc == 8) B200_COLS(1, 4, 8); else B200_COLS(1, 4, 1); }
+#undef B200_COLS
     } else {
         return fail(B200_E_INVALID, "bad reduction layout %d", d->layout);
     }
