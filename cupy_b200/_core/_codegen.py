@@ -92,9 +92,9 @@ def writes_first(operation, name):
 
 def _tiler_type(variant, nargs, vec, unroll, threads, idx32, spec=0):
     if variant == _lib.EW_FLAT:
-        return 'b200::FlatTiler<%d, %d, %d, %d>' % (nargs, vec, unroll, threads)
+        return 'b200::FlatTiler<%d, %d, %d, %d, %s>' % (nargs, vec, unroll, threads, 'true' if spec else 'false')
     if variant == _lib.EW_ROWWISE:
-        return 'b200::RowTiler<%d, %d, %d, %d, %s>' % (nargs, vec, unroll, threads, 'true' if idx32 else 'false')
+        return 'b200::RowTiler<%d, %d, %d, %d, %s, %dull>' % (nargs, vec, unroll, threads, 'true' if idx32 else 'false', spec)
     if variant == _lib.EW_TILED_TMA:
         return 'b200::TmaTileTiler<%d, %d>' % (nargs, 16 // vec)
     if variant == _lib.EW_TILED_REG:

@@ -318,6 +318,18 @@ def _prod(shape):
     return r
 
 
+def _prebuilt_fits(plan, ops, args):
+    """Prebuilt kernels decide operand kinds at run time, which costs 5-17 % when it matters: by-value
+    scalars (a branch per operand in the load phase) and ROWWISE operands that are not unit-stride.
+    Those calls are specialised by NVRTC instead (the reference compiles every call shape)."""
+    if any(o.kind == _lib.KIND_SCALAR for o in ops):
+        return False
+    if plan.variant == _lib.EW_ROWWISE:
+        last = plan.ndim - 1
+        return all(plan.strides[k][last] == a.dtype.itemsize for k, a in enumerate(args))
+    return True
+
+
 # tunables of the generated kernels (bench/tuning scripts override these)
 tunables = {
     'threads': 256,
@@ -357,6 +369,17 @@ def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stre
         else ('arr', a.dtype.char) if isinstance(a, ndarray) else ('scalar', a.descr.char)
         for a, p in zip(args, params))
     access, min_blocks = 0, 1
+    if variant == _lib.EW_FLAT and plan.staged_mask:
+        access = 1                    # FlatTiler<..., PERIODIC = true>
+    if variant == _lib.EW_ROWWISE:
+        # innermost-stride kind per operand (RowTiler SPEC, 2 bits each): unit / zero / other
+        last = plan.ndim - 1
+        for k, o in enumerate(ops):
+            if o.kind != _lib.KIND_ARRAY:
+                continue
+            si = plan.strides[k][last]
+            isz = args[k].dtype.itemsize
+            access |= (1 if si == isz else 2 if si == 0 else 3) << (2 * k)
     if variant == _lib.EW_TILED_REG:
         # per-operand access, fixed at compile time (RegTileTiler SPEC, 3 bits each): staged /
         # unit along O / other, plus "broadcast along I"; registers a thread's blocks take
@@ -782,6 +805,8 @@ class ufunc:
         # (register-tiled calls are prebuilt for unary ufuncs only; NVRTC fixes each operand's access otherwise)
         if (self._prebuilt is not None and not has_where and self.nout == 1
                 and not (plan.variant == _lib.EW_TILED_REG and self.nin > 1)
+                and not (plan.variant == _lib.EW_FLAT and plan.staged_mask)
+                and _prebuilt_fits(plan, ops, all_args)
                 and all(a.dtype == t if isinstance(a, ndarray) else True for a, t in zip(in_args, op.in_types))
                 and (self._prebuilt == 0 or out_args[0].dtype == op.out_types[0])):
             in_ids = (ctypes.c_int32 * self.nin)(*[_scalar.dtype_id(t) for t in op.in_types])

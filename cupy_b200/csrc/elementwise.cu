@@ -78,17 +78,26 @@ extern "C" __attribute__((visibility("default"))) int b200_ufunc_launch(int ufun
     int unroll = 1;
     switch (plan->variant) {
         case B200_EW_FLAT:
+            // periodic operands (row vector over a dense array) are compiled per call shape by NVRTC
+            if (plan->staged_mask) return fail(B200_E_UNSUPPORTED, "FLAT plans with periodic operands have no prebuilt kernel");
             if (plan->vec >= k->vec) { fn = k->flat_v; eff.vec = k->vec; }
-            else if (plan->staged_mask) return fail(B200_E_UNSUPPORTED, "periodic FLAT plan needs the full-vector kernel");
             else { fn = k->flat_1; eff.vec = 1; }
             unroll = k->unroll_flat;
             break;
-        case B200_EW_ROWWISE:
+        case B200_EW_ROWWISE: {
+            bool all_unit = true;
+            for (int a = 0; a < nargs; ++a) {
+                if (args[a].kind == B200_KIND_SCALAR) all_unit = false;      // by-value operands: NVRTC folds them
+                else if (plan->strides[a][plan->ndim - 1] != b200_dtype_itemsize(args[a].dtype)) all_unit = false;
+            }
+            if (!all_unit)
+                return fail(B200_E_UNSUPPORTED, "ROWWISE plans with broadcast / strided / scalar operands have no prebuilt kernel");
             if (plan->vec >= k->vec && k->vec > 1) { fn = plan->idx32 ? k->row_v32 : k->row_v64; eff.vec = k->vec; }
             else { fn = plan->idx32 ? k->row_132 : k->row_164; eff.vec = 1; }
             unroll = k->unroll_row;
             p.fdiv_chunks = FastDiv(uint32_t(std::min<int64_t>(plan->shape[plan->ndim - 1] / eff.vec, 0xfffffffe)));
             break;
+        }
         case B200_EW_TILED:
             fn = k->tiled;
             break;

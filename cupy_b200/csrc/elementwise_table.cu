@@ -114,10 +114,13 @@ static EwKernels make_kernels() {
     EwKernels k;
     k.flat_v = reinterpret_cast<const void*>(&ew_kernel<FlatTiler<N, V, UF, kEwThreads>, F>);
     k.flat_1 = reinterpret_cast<const void*>(&ew_kernel<FlatTiler<N, 1, UF, kEwThreads>, F>);
-    k.row_v32 = reinterpret_cast<const void*>(&ew_kernel<RowTiler<N, V, UR, kEwThreads, true>, F>);
+    // vector ROWWISE kernels are prebuilt for the all-unit-stride case (padded / sliced rows); calls with
+    // broadcast or strided operands are specialised by NVRTC (run-time stride branches cost 10-17 %)
+    constexpr uint64_t kAllUnit = N == 2 ? 0x5ull : N == 3 ? 0x15ull : 0x55ull;
+    k.row_v32 = reinterpret_cast<const void*>(&ew_kernel<RowTiler<N, V, UR, kEwThreads, true, kAllUnit>, F>);
     k.row_132 = reinterpret_cast<const void*>(&ew_kernel<RowTiler<N, 1, UR, kEwThreads, true>, F>);
     k.row_164 = reinterpret_cast<const void*>(&ew_kernel<RowTiler<N, 1, UR, kEwThreads, false>, F>);
-    k.row_v64 = reinterpret_cast<const void*>(&ew_kernel<RowTiler<N, V, UR, kEwThreads, false>, F>);
+    k.row_v64 = reinterpret_cast<const void*>(&ew_kernel<RowTiler<N, V, UR, kEwThreads, false, kAllUnit>, F>);
     k.tiled = reinterpret_cast<const void*>(&ew_kernel<TileTiler<N>, F>);
     k.tiled_tma = TmaKernelOf<F, tma_eligible<F>()>::get();
     k.tiled_reg = RegKernelOf<F, tma_eligible<F>() && F::nin == 1>::get();

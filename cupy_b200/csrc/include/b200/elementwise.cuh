@@ -66,7 +66,9 @@ B200_DEVICE T scalar_arg(const EwParams& p, int a) {
 // consecutive bytes (128-bit accesses when VEC*sizeof(T) >= 16).  Persistent
 // grid-stride over tiles.
 // ---------------------------------------------------------------------------
-template <int NARGS, int VEC, int UNROLL, int THREADS>
+// PERIODIC (compile time: the plain form must not carry its branches, they break the compiler's
+// load batching): some operands are row vectors broadcast over the rows of a dense array.
+template <int NARGS, int VEC, int UNROLL, int THREADS, bool PERIODIC = false>
 struct FlatTiler {
     static constexpr int kV = VEC, kU = UNROLL;
     static constexpr int64_t kTile = int64_t(THREADS) * VEC * UNROLL;
@@ -82,7 +84,7 @@ struct FlatTiler {
         // FLAT with periodic operands (p.staged_mask, period p.tile_axis elements): a row vector
         // broadcast over a dense array.  The host guarantees THREADS * VEC % period == 0, so the
         // element (base + (u * THREADS + tid) * VEC) % period does not depend on the tile or on u.
-        poff = p.staged_mask ? int((int64_t(threadIdx.x) * VEC) % p.tile_axis) : 0;
+        poff = PERIODIC ? int((int64_t(threadIdx.x) * VEC) % p.tile_axis) : 0;
     }
     B200_DEVICE bool valid() const { return base < p.size; }
     B200_DEVICE void next() {
@@ -99,7 +101,7 @@ struct FlatTiler {
     template <bool FULL, class T>
     B200_DEVICE void load(int a, Pack<T, VEC> (&r)[UNROLL]) const {
         const T* __restrict__ ptr = reinterpret_cast<const T*>(p.arg[a].ptr);
-        if ((p.staged_mask >> a) & 1u) {
+        if (PERIODIC && ((p.staged_mask >> a) & 1u)) {
             // periodic operand: one vector serves every unroll step (period % VEC == 0: never straddles)
             Pack<T, VEC> v;
             load_pack(v, ptr + poff);
@@ -158,7 +160,11 @@ struct FlatTiler {
 template <bool IDX32> struct row_offset { typedef int64_t type; };
 template <> struct row_offset<true> { typedef int32_t type; };      // the planner guarantees every span < 2^31
 
-template <int NARGS, int VEC, int UNROLL, int THREADS, bool IDX32>
+// SPEC: two bits per operand fixing its innermost-stride kind at compile time (NVRTC kernels know
+// it; 0 = decide at run time): 1 = unit stride (vector access), 2 = stride 0 (one scalar, broadcast
+// to the lanes), 3 = other (scalar accesses).  Without the run-time branches the compiler batches all
+// loads of a tile ahead of the arithmetic.
+template <int NARGS, int VEC, int UNROLL, int THREADS, bool IDX32, uint64_t SPEC = 0>
 struct RowTiler {
     static constexpr int kV = VEC, kU = UNROLL;
     typedef typename row_offset<IDX32>::type off_t;
@@ -235,14 +241,15 @@ struct RowTiler {
 
     template <bool FULL, class T>
     B200_DEVICE void load(int a, Pack<T, VEC> (&r)[UNROLL]) const {
-        const int64_t si = p.arg[a].strides[p.ndim - 1];
+        const uint32_t kind = uint32_t(SPEC >> (2 * a)) & 3u;
+        const int64_t si = kind == 1 ? int64_t(sizeof(T)) : kind == 2 ? 0 : p.arg[a].strides[p.ndim - 1];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             if (!FULL && !ok[u]) continue;
             const char* base = p.arg[a].ptr + off[u][a];
-            if (VEC > 1 && si == int64_t(sizeof(T))) {
+            if (VEC > 1 && (kind == 1 || (kind == 0 && si == int64_t(sizeof(T))))) {
                 load_pack(r[u], reinterpret_cast<const T*>(base));
-            } else if (VEC > 1 && si == 0) {
+            } else if (VEC > 1 && (kind == 2 || (kind == 0 && si == 0))) {
                 const T v = *reinterpret_cast<const T*>(base);
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) r[u][k] = v;
@@ -254,12 +261,13 @@ struct RowTiler {
     }
     template <bool FULL, class T>
     B200_DEVICE void store(int a, const Pack<T, VEC> (&r)[UNROLL]) const {
-        const int64_t si = p.arg[a].strides[p.ndim - 1];
+        const uint32_t kind = uint32_t(SPEC >> (2 * a)) & 3u;
+        const int64_t si = kind == 1 ? int64_t(sizeof(T)) : p.arg[a].strides[p.ndim - 1];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             if (!FULL && !ok[u]) continue;
             char* base = p.arg[a].ptr + off[u][a];
-            if (VEC > 1 && si == int64_t(sizeof(T))) {
+            if (VEC > 1 && (kind == 1 || (kind == 0 && si == int64_t(sizeof(T))))) {
                 store_pack(reinterpret_cast<T*>(base), r[u]);
             } else {
 #pragma unroll
