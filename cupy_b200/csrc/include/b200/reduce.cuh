@@ -212,8 +212,9 @@ __device__ __forceinline__ void reduce_rows_body(
                         static_cast<index_t>(1));
             }
             // whole vectors that do not fill an unrolled batch: one 16-byte load per lane and step
-            // (rows shorter than GROUP * VEC * UNROLL live here entirely)
-            if (VEC > 1) {
+            // (rows shorter than GROUP * VEC * UNROLL live here entirely).  Small groups only: in the
+            // long-row instantiations the extra lane states cost registers (fp16 var -15 %) for nothing.
+            if (VEC > 1 && GROUP <= 8) {
                 for (; base + int64_t(GROUP) * VEC <= n; base += int64_t(GROUP) * VEC) {
                     Pack<typename Op::in_t, VEC> v1;
                     load_pack(v1, xr + base + int64_t(g) * VEC);
