@@ -129,6 +129,11 @@ static size_t scan_ws_bytes(int64_t n, size_t acc_size) {
     return 16 + align_up(4 * tiles, 16) + 2 * align_up(acc_size * tiles, 16);
 }
 
+// scan_axis.cu: flat scan as (line totals, carry scan, line scans) for the dtype pairs the TMA scan skips
+template <class In, class Acc, class Out, class Op>
+int scan_flat_lines(const In* x, Out* y, int64_t n, void* ws, size_t ws_bytes, int sm_count, cudaStream_t s);
+constexpr int64_t kFlatLinesMinN = int64_t(1) << 18;
+
 template <class In, class Acc, class Out>
 static int run(int op, const void* x, void* y, int64_t n, void* wsp, size_t ws_bytes, cudaStream_t stream) {
     if (reinterpret_cast<uintptr_t>(x) % 16 || reinterpret_cast<uintptr_t>(y) % 16)
@@ -136,6 +141,17 @@ static int run(int op, const void* x, void* y, int64_t n, void* wsp, size_t ws_b
     if constexpr (tma_eligible<In, Acc, Out>::value) {
         const int st = run_tma<In>(op, x, y, n, wsp, ws_bytes, stream);
         if (st != B200_E_UNSUPPORTED) return st;
+    }
+    if (n >= kFlatLinesMinN && getenv("B200_SCAN_LOOKBACK") == nullptr) {
+        DeviceInfo di;
+        int st = device_info(&di);
+        if (st) return st;
+        const In* xi = static_cast<const In*>(x);
+        Out* yo = static_cast<Out*>(y);
+        st = op == B200_OP_CUMSUM ? scan_flat_lines<In, Acc, Out, ScanSum>(xi, yo, n, wsp, ws_bytes, di.sm_count, stream)
+                                  : scan_flat_lines<In, Acc, Out, ScanProd>(xi, yo, n, wsp, ws_bytes, di.sm_count, stream);
+        if (st == 0) { B200_CUDA_TRY(cudaPeekAtLastError()); return 0; }
+        if (st != B200_E_WORKSPACE) return st;       // too little workspace: the look-back kernel below
     }
     const size_t tiles = size_t(scan_tiles(n));
     const size_t need = scan_ws_bytes(n, sizeof(Acc));

@@ -207,6 +207,12 @@ def main():
         xf = cp.from_torch(randn((n,), torch.float32)); yf = cp.empty((n,), np.float32)
         report('cumsum f32 2^28', 8 * n, lambda: cp.cumsum(xf, out=yf), iters=10)
         report('torch cumsum int64 2^28', 16 * n, lambda: torch.cumsum(xi.to_torch(), 0), iters=5)
+        x32 = cp.from_torch(torch.randint(-100, 100, (n,), device='cuda', dtype=torch.int32))
+        report('cumsum int32 -> int64 2^28 (casting, flat)', 12 * n, lambda: cp.cumsum(x32, out=yo), iters=10)
+        xh = cp.from_torch((torch.rand(n, device='cuda') / 1024).to(torch.float16)); yh = cp.empty((n,), np.float16)
+        report('cumsum float16 2^28 (float accumulator, flat)', 4 * n, lambda: cp.cumsum(xh, out=yh), iters=10)
+        xb = cp.from_torch(torch.rand(n, device='cuda') > 0.5)
+        report('cumsum bool -> int64 2^28', 9 * n, lambda: cp.cumsum(xb, out=yo), iters=10)
 
 
 if __name__ == '__main__':
