@@ -43,7 +43,7 @@ def _acc_size(reduce_type, type_map):
 
 
 def _functor_source(kernel, in_args, in_params, out_args, out_params, type_map, map_expr, reduce_expr,
-                    post_map_expr, reduce_type, index64, structured):
+                    post_map_expr, reduce_type, index64, structured, kinds=None, layout_kind=None):
     lines = [_PROLOGUE]
     lines.append('typedef %s IndexT;' % ('long long' if index64 else 'int'))
     for ctype, dt in type_map:
@@ -53,21 +53,44 @@ def _functor_source(kernel, in_args, in_params, out_args, out_params, type_map, 
     lines.append('static_assert(sizeof(_type_reduce) <= %d, "reduce_type too large");' % _MAX_ACC_BYTES)
     multi = [a for a in in_args if isinstance(a, ndarray)] if structured else []
     if len(multi) > 1:
+        # kinds: 0 = laid out like x, 1 = broadcast along the reduced axes (dense over the kept ones),
+        # 2 = broadcast along the kept axes (dense over the reduced ones); see _reduction._operand_kinds
+        ks = tuple(kinds) if kinds is not None else (0,) * len(multi)
+        cols = layout_kind == _lib.RED_COLS
         ts = [get_typename(a.dtype) for a in multi]
         k_all = range(len(multi))
+
+        def step(fmt_by_kind):
+            return ' '.join(fmt_by_kind[ks[k]].format(k=k) for k in k_all)
+
         lines.append('struct __align__(16) _In { %s };' % ' '.join('%s m%d;' % (t, k) for k, t in enumerate(ts)))
         lines.append('struct _InPtr {')
         lines.append('  ' + ' '.join('const %s* p%d;' % (t, k) for k, t in enumerate(ts)))
+        # + / []: a step along the contiguous reduced axis (FULL and ROWS skeletons)
         lines.append('  __device__ __forceinline__ _InPtr operator+(long long _o) const { _InPtr _r; %s return _r; }'
-                     % ' '.join('_r.p%d = p%d + _o;' % (k, k) for k in k_all))
+                     % step({0: '_r.p{k} = p{k} + _o;', 1: '_r.p{k} = p{k};', 2: '_r.p{k} = p{k} + _o;'}))
         lines.append('  __device__ __forceinline__ _In operator[](long long _i) const { _In _r; %s return _r; }'
-                     % ' '.join('_r.m%d = p%d[_i];' % (k, k) for k in k_all))
+                     % step({0: '_r.m{k} = p{k}[_i];', 1: '_r.m{k} = p{k}[0];', 2: '_r.m{k} = p{k}[_i];'}))
         lines.append('};')
+        lines.append('__device__ __forceinline__ _InPtr row_ptr(const _InPtr& _x, long long _row, long long _n) { _InPtr _r; %s return _r; }'
+                     % step({0: '_r.p{k} = _x.p{k} + _row * _n;', 1: '_r.p{k} = _x.p{k} + _row;', 2: '_r.p{k} = _x.p{k};'}))
+        lines.append('__device__ __forceinline__ _InPtr cols_ptr(const _InPtr& _x, long long _b, long long _n, long long _c, long long _c0) '
+                     '{ _InPtr _r; %s return _r; }'
+                     % step({0: '_r.p{k} = _x.p{k} + _b * _n * _c + _c0;', 1: '_r.p{k} = _x.p{k} + _b * _c + _c0;',
+                             2: '_r.p{k} = _x.p{k};'}))
+        lines.append('__device__ __forceinline__ _InPtr cols_row(const _InPtr& _x, long long _rw, long long _c) { _InPtr _r; %s return _r; }'
+                     % step({0: '_r.p{k} = _x.p{k} + _rw * _c;', 1: '_r.p{k} = _x.p{k};', 2: '_r.p{k} = _x.p{k} + _rw;'}))
         lines.append('template <int _N> __device__ __forceinline__ void load_pack(b200::Pack<_In, _N>& _d, const _InPtr& _p) {')
+        scalar_kind = 2 if cols else 1       # one value serves the whole pack
         for k, t in enumerate(ts):
-            lines.append('  { b200::Pack<%s, _N> _t; b200::load_pack(_t, _p.p%d);' % (t, k))
-            lines.append('#pragma unroll')
-            lines.append('    for (int _i = 0; _i < _N; ++_i) _d[_i].m%d = _t[_i]; }' % k)
+            if ks[k] == scalar_kind:
+                lines.append('  { const %s _s = *_p.p%d;' % (t, k))
+                lines.append('#pragma unroll')
+                lines.append('    for (int _i = 0; _i < _N; ++_i) _d[_i].m%d = _s; }' % k)
+            else:
+                lines.append('  { b200::Pack<%s, _N> _t; b200::load_pack(_t, _p.p%d);' % (t, k))
+                lines.append('#pragma unroll')
+                lines.append('    for (int _i = 0; _i < _N; ++_i) _d[_i].m%d = _t[_i]; }' % k)
         lines.append('}')
     lines.append('struct _Op {')
     lines.append('  typedef _type_reduce acc_t; typedef IndexT index_t; struct ctx_t {};')
@@ -168,10 +191,15 @@ def _pick_vec(ptr, inner, itemsize, full):
 
 
 def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_map,
-                      map_expr, reduce_expr, post_map_expr, reduce_type, stream):
+                      map_expr, reduce_expr, post_map_expr, reduce_type, stream, kinds=None):
     xs = [a for a in in_args if isinstance(a, ndarray)]
-    x = xs[0]
-    isz = max(a.dtype.itemsize for a in xs)          # the widest operand sets the vector width
+    kinds = tuple(kinds) if kinds is not None else (0,) * len(xs)
+    x = xs[kinds.index(0)]
+    kind = layout.kind
+    # operands read with vector loads in this layout (the others are one scalar per row / per column pack)
+    vec_kinds = (0, 2) if kind != _lib.RED_COLS else (0, 1)
+    vxs = [a for a, k in zip(xs, kinds) if k in vec_kinds]
+    isz = max(a.dtype.itemsize for a in vxs)         # the widest vector operand sets the vector width
     acc_size = _acc_size(reduce_type, type_map)
     known = acc_size is not None
     acc_bytes = acc_size if known else _MAX_ACC_BYTES
@@ -179,12 +207,11 @@ def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_ma
     sm = _sm_count()
     full_vec = min(16 // isz, 8) if known and acc_bytes <= 16 else 1
     unroll = 2 if full_vec >= 8 else 4
-    kind = layout.kind
     a0 = a1 = a2 = 0
     grid = (1, 1, 1)
     ws_need = 0
     if kind == _lib.RED_FULL:
-        vec = _pick_vec([a.ptr for a in xs], layout.n_reduce, [a.dtype.itemsize for a in xs], full_vec)
+        vec = _pick_vec([a.ptr for a in vxs], layout.n_reduce, [a.dtype.itemsize for a in vxs], full_vec)
         vec = vec if vec == full_vec else 1
         tile = _THREADS * vec * unroll
         g = max(1, min((layout.n_reduce + tile - 1) // tile, sm * 8))
@@ -195,7 +222,7 @@ def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_ma
                 'reinterpret_cast<_Op::acc_t*>(p.ws0), reinterpret_cast<uint32_t*>(p.ws1));' % (vec, unroll, _THREADS))
         tag = 'full_v%d' % vec
     elif kind == _lib.RED_ROWS:
-        vec = _pick_vec([a.ptr for a in xs], layout.n_reduce, [a.dtype.itemsize for a in xs], full_vec)
+        vec = _pick_vec([a.ptr for a in vxs], layout.n_reduce, [a.dtype.itemsize for a in vxs], full_vec)
         vec = vec if vec == full_vec else 1
         n = layout.n_reduce
         # == rows_group() in csrc/reduce_impl.cuh: the largest group whose unrolled batch fits the row
@@ -210,7 +237,7 @@ def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_ma
         cv = full_vec
         while cv > 1 and 8 * 32 * cv * acc_bytes > 32768:
             cv >>= 1
-        vec = _pick_vec([a.ptr for a in xs], layout.n_out, [a.dtype.itemsize for a in xs], cv)
+        vec = _pick_vec([a.ptr for a in vxs], layout.n_out, [a.dtype.itemsize for a in vxs], cv)
         vec = vec if vec == cv else 1
         ru = 2 if vec >= 8 else 4
         wc = 8 if layout.n_out >= 8 * 32 * vec * 2 else 1      # == cols_wc() in csrc/reduce_impl.cuh (plain functors)
@@ -226,13 +253,14 @@ def launch_structured(kernel, layout, in_args, out, in_types, out_types, type_ma
                 'reinterpret_cast<_Op::acc_t*>(p.ws0), reinterpret_cast<uint32_t*>(p.ws1));' % (vec, ru, wc))
         tag = 'cols_v%d_w%d' % (vec, wc)
 
-    key = ('s', tag, index64, tuple(a.dtype.char for a in xs), out.dtype.char, type_map, reduce_type,
+    key = ('s', tag, index64, tuple(a.dtype.char for a in xs), kinds, out.dtype.char, type_map, reduce_type,
            tuple(a.descr.char for a in in_args if isinstance(a, CScalar)))
     fn = kernel._memo.get(key)
     name = kernel.name + '_' + tag
     if fn is None:
         src = _functor_source(kernel, in_args, kernel.in_params, [out], kernel.out_params, type_map,
-                              map_expr, reduce_expr, post_map_expr, reduce_type, index64, True)
+                              map_expr, reduce_expr, post_map_expr, reduce_type, index64, True,
+                              kinds=kinds, layout_kind=kind)
         src += '''
 struct _Params { _Op op; b200::in_ptr<_Op>::type x; _Op::out_t* y; long long a0, a1, a2; void* ws0; void* ws1; };
 extern "C" __global__ void __launch_bounds__(%d) %s(const __grid_constant__ _Params p) {

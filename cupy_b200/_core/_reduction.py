@@ -121,6 +121,37 @@ def _classify(shape, strides, itemsize, reduce_axis, out_axis, ordered_index):
     return generic
 
 
+def _operand_kinds(arrays, x0, layout, reduce_axis, out_axis):
+    """Per array: 0 = laid out like x0, 1 = broadcast along the reduced axes and C-dense over the kept
+    ones, 2 = broadcast along the kept axes and dense over the reduced ones like x0.  None when some
+    operand is none of these (generic kernel)."""
+    shape = x0.shape
+    e0 = [t // x0.dtype.itemsize for t in x0.strides]
+    inner_out = layout.n_out if layout.kind == _lib.RED_COLS else 1      # kept extent inside the reduced run
+    dense_out, st = {}, 1
+    for i in reversed(out_axis):
+        dense_out[i] = st
+        st *= shape[i]
+    kinds = []
+    for a in arrays:
+        isz = a.dtype.itemsize
+        if a.shape != shape or any(t % isz for t in a.strides):
+            return None
+        e = [t // isz for t in a.strides]
+        live = [i for i in range(len(shape)) if shape[i] > 1]
+        if all(e[i] == e0[i] for i in live):
+            kinds.append(0)
+        elif (all(e[i] == 0 for i in reduce_axis if shape[i] > 1)
+              and all(e[i] == dense_out[i] for i in out_axis if shape[i] > 1)):
+            kinds.append(1)
+        elif (layout.kind != _lib.RED_FULL and all(e[i] == 0 for i in out_axis if shape[i] > 1)
+              and all(e[i] * inner_out == e0[i] for i in reduce_axis if shape[i] > 1)):
+            kinds.append(2)
+        else:
+            return None
+    return tuple(kinds)
+
+
 class _AbstractReductionKernel:
 
     def __init__(self, name, identity, in_params, out_params):
@@ -171,17 +202,24 @@ class _AbstractReductionKernel:
         arrays = [a for a in in_args if isinstance(a, ndarray)]
         # structured kernels stream one operand -- or several arrays that share ONE layout (same
         # shape and element strides after broadcasting), as a tuple of their elements
-        x0 = arrays[0] if arrays else None
-        uniform = (len(arrays) >= 1 and len(out_args) == 1
-                   and not any(p.raw for p in self.in_params + self.out_params)
-                   and all(a.shape == x0.shape
-                           and tuple(t // a.dtype.itemsize for t in a.strides) == tuple(t // x0.dtype.itemsize for t in x0.strides)
-                           and all(t % a.dtype.itemsize == 0 for t in a.strides)
-                           for a in arrays))
-        single = uniform and len(arrays) == 1
+        # structured kernels stream one operand -- or several arrays as a tuple of their elements: those
+        # laid out like the first full-size one (kind 0), and those broadcast along the reduced axes
+        # (kind 1: dense over the kept axes, e.g. a keepdims mean) or along the kept axes (kind 2: dense over
+        # the reduced axes, e.g. weights)
         layout = Layout(-1, 1, n_reduce, n_out)
-        if uniform and n_reduce > 0:
-            layout = _classify(x0.shape, x0.strides, x0.dtype.itemsize, reduce_axis, out_axis, self._ordered_index)
+        kinds = None
+        plain = (len(arrays) >= 1 and len(out_args) == 1 and n_reduce > 0
+                 and not any(p.raw for p in self.in_params + self.out_params))
+        if plain:
+            x0 = next((a for a in arrays if 0 not in [t for t, n_ in zip(a.strides, a.shape) if n_ > 1]), None)
+            if x0 is not None:
+                layout = _classify(x0.shape, x0.strides, x0.dtype.itemsize, reduce_axis, out_axis, self._ordered_index)
+                if layout.kind >= 0:
+                    kinds = _operand_kinds(arrays, x0, layout, reduce_axis, out_axis)
+                    if kinds is None:
+                        layout = Layout(-1, 1, n_reduce, n_out)
+        uniform = kinds is not None
+        single = uniform and len(arrays) == 1
 
         # the fast layouts write a dense C-ordered result of the loop's natural dtype
         out = out_args[0]
@@ -213,7 +251,7 @@ class _AbstractReductionKernel:
             if uniform:
                 _codegen_reduce.launch_structured(
                     self, layout, in_args, target, in_types, out_types, type_map,
-                    map_expr, reduce_expr, post_map_expr, reduce_type, st)
+                    map_expr, reduce_expr, post_map_expr, reduce_type, st, kinds=kinds)
                 if target is not out:
                     _kernel.elementwise_copy(target.reshape(out.shape), out)
                 return ret

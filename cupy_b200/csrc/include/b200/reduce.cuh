@@ -33,6 +33,15 @@ template <class T> struct void_of { typedef void type; };
 template <class Op, class = void> struct in_ptr { typedef const typename Op::in_t* __restrict__ type; };
 template <class Op> struct in_ptr<Op, typename void_of<typename Op::ptr_t>::type> { typedef typename Op::ptr_t type; };
 
+// Pointer steps of the ROWS / COLS skeletons, as hooks: a pointer struct whose members are not all
+// laid out like x (operands broadcast along the reduced or the kept axes: `x - mean`, weights) brings
+// its own overloads.
+template <class P> B200_DEVICE P row_ptr(const P& x, int64_t row, int64_t n) { return x + row * n; }
+template <class P> B200_DEVICE P cols_ptr(const P& x, int64_t b, int64_t n, int64_t cols, int64_t c0) {
+    return x + b * n * cols + c0;
+}
+template <class P> B200_DEVICE P cols_row(const P& xb, int64_t r, int64_t cols) { return xb + r * cols; }
+
 template <class T>
 B200_DEVICE T load_volatile(const T* p) {
     // accumulators published by other blocks: read around L1, in words when possible
@@ -200,7 +209,7 @@ __device__ __forceinline__ void reduce_rows_body(
          row0 += int64_t(gridDim.x) * kRowsPerBlock) {
         const int64_t row = row0 + gi;
         const bool live = row < rows;
-        const typename in_ptr<Op>::type xr = x + (live ? row : 0) * n;
+        const typename in_ptr<Op>::type xr = row_ptr(x, live ? row : 0, n);
         ThreadAcc<Op, UNROLL, VEC> ta(op);
         if (live) {
             int64_t base = 0;
@@ -275,7 +284,7 @@ __device__ __forceinline__ void reduce_cols_body(
     const int64_t rows_per_split = (n + nsplit - 1) / nsplit;
     const int64_t r_begin = int64_t(split) * rows_per_split;
     const int64_t r_end = (r_begin + rows_per_split < n) ? r_begin + rows_per_split : n;
-    const typename in_ptr<Op>::type xb = x + b * n * cols + c0;
+    const typename in_ptr<Op>::type xb = cols_ptr(x, b, n, cols, c0);
 
     ThreadAcc<Op, RU, VEC> ta(op);
     if (col_ok) {
@@ -283,12 +292,12 @@ __device__ __forceinline__ void reduce_cols_body(
         for (; r + int64_t(RU - 1) * kWarpRows < r_end; r += int64_t(RU) * kWarpRows) {
             Pack<typename Op::in_t, VEC> v[RU];
 #pragma unroll
-            for (int u = 0; u < RU; ++u) load_pack(v[u], xb + (r + int64_t(u) * kWarpRows) * cols);
+            for (int u = 0; u < RU; ++u) load_pack(v[u], cols_row(xb, r + int64_t(u) * kWarpRows, cols));
             ta.fold(v, static_cast<index_t>(r), static_cast<index_t>(kWarpRows), static_cast<index_t>(0));
         }
         for (; r < r_end; r += kWarpRows) {
             Pack<typename Op::in_t, VEC> v;
-            load_pack(v, xb + r * cols);
+            load_pack(v, cols_row(xb, r, cols));
 #pragma unroll
             for (int k = 0; k < VEC; ++k) ta.fold_one_lane(k, v[k], static_cast<index_t>(r));
         }

@@ -185,6 +185,13 @@ def main():
             report('ReductionKernel dot(x,y) axis=%s f32 16384^2' % ax, 8 * m * m, lambda: dot(xa, xb, axis=ax), iters=10)
         fr = cp.fuse(kernel_name='fuse_sqdiff')(lambda x, y: cp.sum((x - y) * (x - y), axis=1))
         report('cupy_b200.fuse sum((x-y)^2, axis=1) 16384^2', 8 * m * m, lambda: fr(xa, xb), iters=10)
+        ssd = cp.ReductionKernel('T x, T m', 'T z', '(x - m) * (x - m)', 'a + b', 'z = a', '0', 'sum_sq_dev')
+        for ax in (1, 0):
+            mk = xa.mean(axis=ax, keepdims=True)
+            report('ReductionKernel sum((x-mean)^2) axis=%d (broadcast mean) 16384^2' % ax, 4 * m * m,
+                   lambda: ssd(xa, mk, axis=ax), iters=10)
+            report('var(axis=%d, dtype=float32 given: two-pass reference algorithm)' % ax, 8 * m * m,
+                   lambda: xa.var(axis=ax, dtype=np.float32), iters=10)
         report('torch (x*y).sum(1) 16384^2 (2 kernels)', 8 * m * m, lambda: (xa.to_torch() * xb.to_torch()).sum(1), iters=5)
         del xa, xb
     if 'axis' in which:

@@ -287,7 +287,10 @@ def test_reduction_routes(dry):
     dot = cp.ReductionKernel('T x, T y', 'T z', 'x * y', 'a + b', 'z = a', '0', 'dot')
     dot(a, a, axis=1)                                   # two arrays of ONE layout: structured, tuple operand
     assert 'rows' in dry[-1]['name'] and '_InPtr' in dry[-1].get('source', '_InPtr')
-    dot(a, a[0], axis=1)                                # a broadcast operand has another layout -> generic kernel
+    dot(a, a[0], axis=1)                                # a row vector broadcast over the kept axis: still structured
+    assert 'rows' in dry[-1]['name']
+    sq = cp.empty((64, 64), 'f')
+    dot(sq, sq.T, axis=1)                               # operands of different layouts -> generic kernel
     assert 'generic' in dry[-1]['name']
 
 

@@ -600,3 +600,40 @@ def test_row_vector_broadcast_periodic_flat(cp, shape, dt):
     # misaligned views leave the periodic path
     if shape[-1] >= 8:
         np.testing.assert_array_equal((d[..., 1:] + dv[1:]).get(), a[..., 1:] + v[1:])
+
+
+@pytest.mark.parametrize('shape,axis', [((300, 1000), 1), ((300, 1000), 0), ((7, 65, 33), 1), ((7, 65, 33), (0, 2)),
+                                        ((4, 5, 2048), 2), ((5, 70000), 1), ((3000, 6), 0), ((6, 9, 10), (1, 2))])
+def test_reduction_kernel_broadcast_operands(cp, shape, axis):
+    """Operands broadcast along the reduced axes (a keepdims mean: the reference's own variance
+    kernel `_var_core_out`, cupy/_core/_routines_statistics.pyx:611-643) or along the kept axes
+    (weights) stay on the structured skeletons."""
+    x = rnd(shape, 'float32')
+    x64 = x.astype(np.float64)
+    m = x64.mean(axis=axis, keepdims=True).astype(np.float32)
+    ssd = cp.ReductionKernel('T x, T m', 'T z', '(x - m) * (x - m)', 'a + b', 'z = a', '0', 'sum_sq_dev')
+    got = ssd(cp.asarray(x), cp.asarray(m), axis=axis).get()
+    want = ((x64 - m) ** 2).sum(axis=axis)
+    np.testing.assert_allclose(got, want, rtol=2e-5)
+    # weights along the reduced axes, broadcast over the kept ones
+    ax = (axis,) if isinstance(axis, int) else axis
+    wshape = tuple(s if i in ax else 1 for i, s in enumerate(shape))
+    w = rnd(wshape, 'float32')
+    wsum = cp.ReductionKernel('T x, T w', 'T z', 'x * w', 'a + b', 'z = a', '0', 'weighted_sum')
+    got = wsum(cp.asarray(x), cp.asarray(w), axis=axis, keepdims=True).get()
+    np.testing.assert_allclose(got, (x64 * w).sum(axis=axis, keepdims=True), rtol=1e-4, atol=1e-3)
+    # all three kinds at once, mixed dtypes
+    k3 = cp.ReductionKernel('float32 x, float64 m, float32 w', 'float64 z', '(x - m) * w', 'a + b', 'z = a', '0',
+                            'centred_weighted', reduce_type='double')
+    m64 = x64.mean(axis=axis, keepdims=True)
+    got = k3(cp.asarray(x), cp.asarray(m64), cp.asarray(w), axis=axis).get()
+    np.testing.assert_allclose(got, ((x64 - m64) * w).sum(axis=axis), rtol=1e-6, atol=1e-6)
+    # the public var with dtype= / out= runs the reference's two-pass algorithm through this path
+    d = cp.asarray(x)
+    np.testing.assert_allclose(d.var(axis=axis, dtype=np.float64).get(), x64.var(axis=axis), rtol=1e-6)
+    out = cp.empty(np.var(x, axis=axis).shape, np.float32)
+    d.var(axis=axis, out=out, ddof=1)
+    np.testing.assert_allclose(out.get(), x64.var(axis=axis, ddof=1), rtol=2e-5)
+    # through cupy_b200.fuse
+    f = cp.fuse(kernel_name='fused_ssd')(lambda a, b: cp.sum((a - b) * (a - b), axis=axis))
+    np.testing.assert_allclose(f(d, cp.asarray(m)).get(), want, rtol=2e-5)
