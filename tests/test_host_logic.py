@@ -347,3 +347,83 @@ def test_codegen_skips_the_load_of_write_first_outputs(dry):
     assert 'load<_FULL>(1' not in dry[-1]['source']
     cp.ElementwiseKernel('T x', 'T z', 'z += x', 'wf_b')(x, cp.empty((1 << 16,), 'f'))
     assert 'load<_FULL>(1' in dry[-1]['source']
+
+
+# ---- fusion, operand kinds, axis scans (host logic; no GPU) -----------------------------------
+def test_fuse_traces_into_one_kernel(dry):
+    @cp.fuse(kernel_name='fused_probe')
+    def f(x, v):
+        return cp.exp(x) + v * 2
+
+    xt = cp.empty((16, 64, 128), 'f').transpose(2, 1, 0)
+    r = f(xt, cp.empty((16,), 'f'))
+    assert r.shape == (128, 64, 16) and r.dtype == np.float32
+    assert len(dry) == 1 and dry[0]['kind'] == 'jit_elementwise' and dry[0]['variant'] == _lib.EW_TILED_REG
+    src = dry[0]['source']
+    assert 'out0 = exp(in0)' in src and 'out0 = in0 * in1' in src and 'out0 = in0 + in1' in src
+    assert 'load<_FULL>(2' not in src                      # the output is write-only
+    del dry[:]
+    f(xt, cp.empty((16,), 'f'))                            # second call: cached trace, one launch again
+    assert len(dry) == 1
+    # weak Python scalars keep the array dtype (NEP 50), NumPy scalars promote
+    assert cp.fuse(lambda x: x * 2 + 1)(cp.empty((8,), 'e')).dtype == np.float16
+    assert cp.fuse(lambda x: x * np.float64(2))(cp.empty((8,), 'f')).dtype == np.float64
+    with pytest.raises(NotImplementedError):
+        cp.fuse(lambda x: cp.sum(x) * 2)(cp.empty((8,), 'f'))
+    with pytest.raises(TypeError):
+        cp.fuse(lambda x: x if x > 0 else x)(cp.empty((8,), 'f'))
+
+
+def test_fused_and_user_reductions_use_the_structured_skeletons(dry):
+    a, b = cp.empty((300, 1000), 'f'), cp.empty((300, 1000), 'f')
+    f = cp.fuse(kernel_name='fused_ssd_probe')(lambda x, y: cp.sum((x - y) * (x - y), axis=1))
+    r = f(a, b)
+    assert r.shape == (300,) and dry[-1]['kind'] == 'jit_reduce' and 'rows' in dry[-1]['name']
+    f0 = cp.fuse(kernel_name='fused_ssd_probe0')(lambda x, y: cp.sum((x - y) * (x - y), axis=0))
+    f0(a, b)
+    assert 'cols' in dry[-1]['name']
+    # operand kinds: keepdims mean (1), weights along the reduced axis (2)
+    from cupy_b200._core import _reduction
+    m = cp.empty((300, 1), 'f')
+    w = cp.empty((1, 1000), 'f')
+    ssd = cp.ReductionKernel('T x, T m, T w', 'T z', '(x - m) * w', 'a + b', 'z = a', '0', 'kinds_probe')
+    ssd(a, m, w, axis=1)
+    assert 'rows' in dry[-1]['name']
+    from cupy_b200._core._ndarray import ndarray as _nd
+    bm, bw = (m * cp.empty((1, 1), 'f')).shape, None       # noqa: F841  (broadcast happens inside the kernel call)
+    lay = _reduction._classify(a.shape, a.strides, 4, (1,), (0,), False)
+    import numpy
+    ms = _nd((300, 1000), 'f', memptr=m.ptr, strides=(4, 0))
+    ws = _nd((300, 1000), 'f', memptr=w.ptr, strides=(0, 4))
+    assert _reduction._operand_kinds([a, ms, ws], a, lay, (1,), (0,)) == (0, 1, 2)
+    assert _reduction._operand_kinds([a, a.T.copy().T], a, lay, (1,), (0,)) is None
+    lay0 = _reduction._classify(a.shape, a.strides, 4, (0,), (1,), False)
+    m0 = _nd((300, 1000), 'f', memptr=w.ptr, strides=(0, 4))          # keepdims mean over axis 0
+    w0 = _nd((300, 1000), 'f', memptr=m.ptr, strides=(4, 0))          # weights along axis 0
+    assert _reduction._operand_kinds([a, m0, w0], a, lay0, (0,), (1,)) == (0, 1, 2)
+
+
+def test_axis_scan_views_the_array_in_place(dry):
+    a = cp.empty((6, 50, 32), 'i')
+    r = cp.cumsum(a, axis=1)
+    assert r.dtype == np.int64 and r.shape == a.shape
+    rec = [d for d in dry if d['kind'] == 'prebuilt_scan_axis'][-1]
+    assert (rec['outer'], rec['n'], rec['inner']) == (6, 50, 32)
+    assert not any(d['kind'] in ('jit_elementwise', 'prebuilt_ufunc') for d in dry)      # no transposing copies
+    del dry[:]
+    cp.cumsum(a.transpose(2, 0, 1), axis=0)                  # a non-dense view is staged once
+    assert sum(d['kind'] in ('jit_elementwise', 'prebuilt_ufunc') for d in dry) == 1
+    assert [d for d in dry if d['kind'] == 'prebuilt_scan_axis'][-1]['inner'] == 6 * 50
+
+
+def test_prebuilt_kernels_serve_only_fixed_operand_kinds(dry):
+    x = cp.empty((1 << 16,), 'f')
+    cp.add(x, x)
+    assert dry[-1]['kind'] == 'prebuilt_ufunc'
+    cp.multiply(x, 2)                                        # by-value scalar -> NVRTC folds it
+    assert dry[-1]['kind'] == 'jit_elementwise' and dry[-1]['variant'] == _lib.EW_FLAT
+    pad = cp.empty((64, 512), 'f')[:, :300]
+    cp.add(pad, pad)                                         # padded rows, all unit stride: prebuilt ROWWISE
+    assert dry[-1]['kind'] == 'prebuilt_ufunc' and dry[-1]['variant'] == _lib.EW_ROWWISE
+    cp.add(pad, cp.empty((64, 1), 'f'))                      # column broadcast: specialised
+    assert dry[-1]['kind'] == 'jit_elementwise' and 'RowTiler' in dry[-1]['source']
