@@ -87,6 +87,24 @@ B200_DEVICE void load_pack(Pack<T, N>& dst, const T* __restrict__ p) {
         reinterpret_cast<V*>(&dst)[c] = reinterpret_cast<const V*>(p)[c];
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256) for packs of exactly 32 bytes whose address is
+// 32-byte aligned: a thread that owns 32 contiguous bytes touches whole sectors with ONE instruction
+// instead of two half-sector ones.
+template <class T, int N>
+B200_DEVICE void load_pack256(Pack<T, N>& dst, const T* __restrict__ p) {
+    static_assert(sizeof(T) * N == 32, "load_pack256 moves exactly 32 bytes");
+    uint64_t a, b, c, d;
+    asm("ld.global.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+    uint64_t* w = reinterpret_cast<uint64_t*>(&dst);
+    w[0] = a; w[1] = b; w[2] = c; w[3] = d;
+}
+template <class T, int N>
+B200_DEVICE void store_pack256(T* __restrict__ p, const Pack<T, N>& src) {
+    static_assert(sizeof(T) * N == 32, "store_pack256 moves exactly 32 bytes");
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&src);
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(w[0]), "l"(w[1]), "l"(w[2]), "l"(w[3]) : "memory");
+}
+
 template <class T, int N>
 B200_DEVICE void store_pack(T* __restrict__ p, const Pack<T, N>& src) {
     constexpr int total = int(sizeof(T)) * N;

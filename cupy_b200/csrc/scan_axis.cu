@@ -25,7 +25,9 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------
 // carry_in (optional): exclusive prefix each line starts from; total (>= 0): the lines are consecutive
 // chunks of a FLAT array of `total` elements, the last one ragged (flat casting scans, see scan_flat_lines).
-template <class In, class Acc, class Out, class Op, int GROUP, int ITEMS>
+// W256 (compile time): 32-byte packs (8-byte items) move with one 256-bit access; the host guarantees
+// 32-byte aligned lines for them.
+template <class In, class Acc, class Out, class Op, int GROUP, int ITEMS, bool W256 = false>
 __global__ void __launch_bounds__(256) scan_lines_kernel(const In* __restrict__ x, Out* __restrict__ y, int64_t lines,
                                                          int64_t n_line, int in_vec, int out_vec,
                                                          const Acc* __restrict__ carry_in, int64_t total) {
@@ -49,7 +51,8 @@ __global__ void __launch_bounds__(256) scan_lines_kernel(const In* __restrict__ 
             Acc item[ITEMS];
             if (live && in_vec && i0 + ITEMS <= n) {
                 Pack<In, ITEMS> v;
-                load_pack(v, xl + i0);
+                if constexpr (W256 && sizeof(In) * ITEMS == 32) load_pack256(v, xl + i0);
+                else load_pack(v, xl + i0);
 #pragma unroll
                 for (int j = 0; j < ITEMS; ++j) item[j] = static_cast<Acc>(v[j]);
             } else {
@@ -87,7 +90,8 @@ __global__ void __launch_bounds__(256) scan_lines_kernel(const In* __restrict__ 
                 Pack<Out, ITEMS> o;
 #pragma unroll
                 for (int j = 0; j < ITEMS; ++j) o[j] = static_cast<Out>(Op::combine(pre, item[j]));
-                store_pack(yl + i0, o);
+                if constexpr (W256 && sizeof(Out) * ITEMS == 32) store_pack256(yl + i0, o);
+                else store_pack(yl + i0, o);
             } else if (live) {
 #pragma unroll
                 for (int j = 0; j < ITEMS; ++j)
@@ -186,7 +190,14 @@ static int run_axis(const void* xv, void* yv, int64_t outer, int64_t n, int64_t 
         constexpr int out_al = int(sizeof(Out)) * ITEMS >= 16 ? 16 : int(sizeof(Out)) * ITEMS;
         const int in_vec = (xa % in_al == 0) && ((n * int64_t(sizeof(In))) % in_al == 0);
         const int out_vec = (ya % out_al == 0) && ((n * int64_t(sizeof(Out))) % out_al == 0);
-        if (n > 32 * ITEMS * 2) {       // long lines: a block per line
+        constexpr bool k256 = sizeof(In) * ITEMS == 32 || sizeof(Out) * ITEMS == 32;
+        const bool w256 = k256 && in_vec && out_vec &&
+                          (sizeof(In) * ITEMS != 32 || (xa % 32 == 0 && (n * int64_t(sizeof(In))) % 32 == 0)) &&
+                          (sizeof(Out) * ITEMS != 32 || (ya % 32 == 0 && (n * int64_t(sizeof(Out))) % 32 == 0));
+        if (n > 32 * ITEMS * 2 && w256) {
+            const unsigned grid = unsigned(std::min<int64_t>(outer, int64_t(sm_count) * 8));
+            scan_lines_kernel<In, Acc, Out, Op, 256, ITEMS, k256><<<grid, 256, 0, s>>>(x, y, outer, n, 1, 1, nullptr, -1);
+        } else if (n > 32 * ITEMS * 2) {       // long lines: a block per line
             const unsigned grid = unsigned(std::min<int64_t>(outer, int64_t(sm_count) * 8));
             scan_lines_kernel<In, Acc, Out, Op, 256, ITEMS><<<grid, 256, 0, s>>>(x, y, outer, n, in_vec, out_vec, nullptr, -1);
         } else {                        // short lines: a warp per line
@@ -304,8 +315,14 @@ int scan_flat_lines(const In* x, Out* y, int64_t n, void* ws, size_t ws_bytes, i
     const int in_vec = xa % 16 == 0, out_vec = ya % out_al == 0;
     line_totals_kernel<In, Acc, Op><<<unsigned(lines), 256, 0, s>>>(x, tot, lines, n_line, n, in_vec);
     carry_scan_kernel<Acc, Op><<<1, 256, 0, s>>>(tot, lines);
-    scan_lines_kernel<In, Acc, Out, Op, 256, ITEMS><<<unsigned(lines), 256, 0, s>>>(x, y, lines, n_line, in_vec && (xa % in_al == 0),
-                                                                                  out_vec, tot, n);
+    constexpr bool k256 = sizeof(In) * ITEMS == 32 || sizeof(Out) * ITEMS == 32;
+    const bool iv = in_vec && (xa % in_al == 0);
+    const bool w256 = k256 && iv && out_vec && (sizeof(In) * ITEMS != 32 || xa % 32 == 0) &&
+                      (sizeof(Out) * ITEMS != 32 || ya % 32 == 0);          // n_line is a multiple of the tile
+    if (w256)
+        scan_lines_kernel<In, Acc, Out, Op, 256, ITEMS, k256><<<unsigned(lines), 256, 0, s>>>(x, y, lines, n_line, 1, 1, tot, n);
+    else
+        scan_lines_kernel<In, Acc, Out, Op, 256, ITEMS><<<unsigned(lines), 256, 0, s>>>(x, y, lines, n_line, iv, out_vec, tot, n);
     return 0;
 }
 
