@@ -8,8 +8,6 @@ FULL / ROWS / COLS skeletons of b200/reduce.cuh like any other `create_reduction
 """
 from __future__ import annotations
 
-import numpy
-
 from cupy_b200._core._reduction import create_reduction_func
 from cupy_b200._core import _routines_math as _math
 from cupy_b200._core import _routines_statistics as _stat

@@ -164,7 +164,6 @@ def sharded_var(x_local, comm, ddof=0):
     numpy.var of the gathered array).  ONE pass over the shard gives (mean, M2)
     (B200_OP_MOMENTS), then one all-gather of 3 doubles per rank and a Chan merge in
     rank order, so every rank computes the bit-identical result."""
-    import ctypes
     import numpy
     from cupy_b200 import _lib
     from cupy_b200._core._ndarray import ndarray

@@ -390,9 +390,7 @@ def test_fused_and_user_reductions_use_the_structured_skeletons(dry):
     ssd(a, m, w, axis=1)
     assert 'rows' in dry[-1]['name']
     from cupy_b200._core._ndarray import ndarray as _nd
-    bm, bw = (m * cp.empty((1, 1), 'f')).shape, None       # noqa: F841  (broadcast happens inside the kernel call)
     lay = _reduction._classify(a.shape, a.strides, 4, (1,), (0,), False)
-    import numpy
     ms = _nd((300, 1000), 'f', memptr=m.ptr, strides=(4, 0))
     ws = _nd((300, 1000), 'f', memptr=w.ptr, strides=(0, 4))
     assert _reduction._operand_kinds([a, ms, ws], a, lay, (1,), (0,)) == (0, 1, 2)
