@@ -345,6 +345,24 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline(1, min_seconds=args.cpu_seconds)
+    # ---- every other BASELINE.json config, device-timed with an in-bench parity check, and the reference's own
+    #      GPU kernels beside them (bench_configs.py).  Not part of `value`; the headline stays axpy + sum.
+    if not args.no_configs:
+        import bench_configs
+        del x, y, z, tx, ty, dx, dy, dz, hx, hy, hz
+        torch.cuda.empty_cache()
+        c5 = bench_configs.run_c5(world, rank, comm, peak)
+        if rank == 0:
+            line['c5'] = c5
+        if world == 1:
+            line['c1_cpu'] = bench_configs.c1_numpy()
+            line['configs'], note = bench_configs.run_configs(peak, with_ref_gpu=not args.no_ref_gpu)
+            if note:
+                line['reference_gpu_unavailable'] = note
+            bad = [e['name'] for e in line['configs'] if 'MISMATCH' in str(e.get('check'))]
+            bad += ['c5 ' + k for k in ('sum', 'var') if 'MISMATCH' in c5[k]['check']]
+            line['configs_parity'] = 'green' if not bad else {'failed': bad}
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -361,6 +379,8 @@ def main():
     ap.add_argument('--e2e-chunks', type=int, default=16)
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='headline only: skip the configs table / c5 record')
+    ap.add_argument('--no-ref-gpu', action='store_true', help='skip the reference-GPU baseline leg of the configs table')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
