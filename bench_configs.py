@@ -224,22 +224,26 @@ def run_configs(peak, with_ref_gpu=True, quick=False):
         # float64 references, one axis at a time, in row slabs (no 8 GiB temporaries)
         s64 = [torch.zeros(m, device='cuda', dtype=torch.float64) for _ in range(2)]
         q64 = [torch.zeros(m, device='cuda', dtype=torch.float64) for _ in range(2)]
+        a64 = [torch.zeros(m, device='cuda', dtype=torch.float64) for _ in range(2)]      # sum |x|
         for lo in range(0, m, 2048):
             c = t[lo:lo + 2048].double()
-            s64[0] += c.sum(0); q64[0] += (c * c).sum(0)
-            s64[1][lo:lo + 2048] = c.sum(1); q64[1][lo:lo + 2048] = (c * c).sum(1)
+            s64[0] += c.sum(0); q64[0] += (c * c).sum(0); a64[0] += c.abs().sum(0)
+            s64[1][lo:lo + 2048] = c.sum(1); q64[1][lo:lo + 2048] = (c * c).sum(1); a64[1][lo:lo + 2048] = c.abs().sum(1)
         for op in ('sum', 'max', 'argmax', 'var'):
             for ax in (0, 1):
                 ms, _ = _median_ms(lambda: getattr(x, op)(axis=ax), iters=it)
                 got = getattr(x, op)(axis=ax).to_torch()
                 if op == 'sum':
+                    # a sum's error scales with sum|x| (the values cancel: |sum| ~ 100, sum|x| = 16384), which is what
+                    # the reference's own CUB-vs-NumPy tests allow for (rtol on shaped_random, test_sumprod.py:213-296)
                     want = s64[ax]
                     if sfx == 'f32':
-                        err = float(((got.double() - want).abs() / want.abs().clamp(min=1.0)).max())
-                        chk = ('ok' if err <= 1e-5 else 'MISMATCH') + ' max_rel_err=%.1e (tol 1e-5)' % err
+                        err = float(((got.double() - want).abs() / a64[ax]).max())
+                        chk = ('ok' if err <= 1e-5 else 'MISMATCH') + ' max_err=%.1e of sum|x| (tol 1e-5)' % err
                     else:
-                        ulps = float(((got.double() - want).abs() / _ulp16(want)).max())
-                        chk = ('ok' if ulps <= 1.0 else 'MISMATCH') + ' max_err=%.2f fp16 ulp (fp32 accumulate; tol 1)' % ulps
+                        # fp32 accumulate, one rounding to fp16 at the end: half an fp16 ulp + the fp32 accumulation error
+                        over = float(((got.double() - want).abs() - 0.5 * _ulp16(want) - 1e-6 * a64[ax]).max())
+                        chk = ('ok' if over <= 0 else 'MISMATCH') + ' |err| <= 0.5 fp16 ulp + 1e-6 sum|x| (fp32 accumulate): margin %.1e' % -over
                 elif op == 'var':
                     mean = s64[ax] / m
                     want = q64[ax] / m - mean * mean
@@ -272,7 +276,7 @@ def run_configs(peak, with_ref_gpu=True, quick=False):
                     except Exception as ex:
                         e['ref_gpu'] = {'error': '%s: %s' % (type(ex).__name__, str(ex)[:200])}
                 entries.append(e)
-        del x, t, s64, q64
+        del x, t, s64, q64, a64
         torch.cuda.empty_cache()
 
     # ---------------- C4a: exp(x^T) + row vector, 1024 x 1024 x 256 f32 ----------------------------
@@ -395,9 +399,10 @@ def run_configs(peak, with_ref_gpu=True, quick=False):
     ms, _ = _median_ms(lambda: cp.cumsum(xh), iters=it)
     goth = cp.cumsum(xh).to_torch()
     wanth = torch.cumsum(th.double(), 0)
-    ulps = float(((goth.double() - wanth).abs() / _ulp16(wanth).clamp(min=2.0 ** -24)).max())
+    # float accumulator, one rounding to fp16 per output: half an fp16 ulp + fp32 accumulation error (of cumsum|x|)
+    over = float(((goth.double() - wanth).abs() - 0.5 * _ulp16(wanth) - 1e-6 * torch.cumsum(th.double().abs(), 0)).max())
     entries.append(_entry('casting cumsum float16 (float accumulate) 2^28', 4 * n, ms, peak,
-                          ('ok' if ulps <= 4.0 else 'MISMATCH') + ' max_err=%.2f fp16 ulp vs float64 scan' % ulps))
+                          ('ok' if over <= 0 else 'MISMATCH') + ' |err| <= 0.5 fp16 ulp + 1e-6 cumsum|x|: margin %.1e' % -over))
     del xh, th, goth, wanth
     torch.cuda.empty_cache()
 

@@ -32,8 +32,8 @@ class EwSpec:
 
     def __init__(self, mode, operation, preamble='', loop_prep='', after_loop='', options=(),
                  in_types=None, out_types=None, has_where=False, type_map=(), write_only_outputs=False):
-        self.mode = mode
-        self.write_only_outputs = write_only_outputs   # generated text (cupy_b200.fuse): outputs are only assigned                  # 'elementwise' (user kernel) | 'ufunc'
+        self.mode = mode                               # 'elementwise' (user kernel) | 'ufunc'
+        self.write_only_outputs = write_only_outputs   # generated text (cupy_b200.fuse): outputs are only assigned
         self.operation = operation
         self.preamble = preamble
         self.loop_prep = loop_prep
@@ -87,7 +87,12 @@ def writes_first(operation, name):
         return False
     before = operation[:m.start()].rstrip()
     after = operation[m.end():].lstrip()
-    return (before == '' or before.endswith(';')) and after.startswith('=') and not after.startswith('==')
+    if not ((before == '' or before.endswith(';')) and after.startswith('=') and not after.startswith('==')):
+        return False
+    # the right-hand side of that first assignment must not read the output (`y = y + x`,
+    # `y = m ? x : y`): the statement ends at the next `;` (no braces / control flow here)
+    rhs = after[1:].split(';', 1)[0]
+    return re.search(r'\b%s\b' % re.escape(name), rhs) is None
 
 
 def _tiler_type(variant, nargs, vec, unroll, threads, idx32, spec=0):
@@ -103,7 +108,9 @@ def _tiler_type(variant, nargs, vec, unroll, threads, idx32, spec=0):
 
 
 def render_elementwise(spec, name, args, params, variant, vec, unroll, threads, idx32, ndim, access_spec=0,
-                       min_blocks=1):
+                       min_blocks=1, ind_ndim=0):
+    """`ind_ndim` > 0: `_ind` is built from the un-collapsed loop shape of that rank (reduce_dims=False
+    kernels), which arrives as one extra shape-only view behind the raw operands."""
     from cupy_b200._core._ndarray import ndarray
     nargs = len(args)
     if variant == _lib.EW_TILED:
@@ -123,9 +130,10 @@ def render_elementwise(spec, name, args, params, variant, vec, unroll, threads, 
     lines.extend(typedefs)
     lines.append(spec.preamble)
     min_blocks = ', %d' % min_blocks if variant == _lib.EW_TILED_REG else ''
+    n_views = sum(1 for a, p in zip(args, params) if isinstance(a, ndarray) and p.raw) + (1 if ind_ndim else 0)
     lines.append('extern "C" __global__ void __launch_bounds__(%d%s) %s('
-                 'const __grid_constant__ b200::EwParams _p, const __grid_constant__ b200::RawPack _rv%s) {'
-                 % (threads, min_blocks, name, ', const __grid_constant__ b200::TileMaps _tm' if tma else ''))
+                 'const __grid_constant__ b200::EwParams _p, const __grid_constant__ b200::RawPackN<%d> _rv%s) {'
+                 % (threads, min_blocks, name, n_views, ', const __grid_constant__ b200::TileMaps _tm' if tma else ''))
     lines.append('  typedef %s _Tiler;' % _tiler_type(variant, nargs, vec, unroll, threads, idx32, access_spec))
     lines.append('  constexpr int _V = _Tiler::kV, _U = _Tiler::kU;')
 
@@ -181,7 +189,10 @@ def render_elementwise(spec, name, args, params, variant, vec, unroll, threads, 
                 t = p.ctype
                 decl.append('  const %s %s = b200::scalar_arg<%s>(_p, %d);' % (t, p.name, t, k))
     lines.extend(decl)
-    lines.append('  CIndexer<%d> _ind(_p.size, _p.shape);' % (ndim if spec.uses_ind else 1))
+    if ind_ndim:
+        lines.append('  CIndexer<%d> _ind(_p.size, _rv.v[%d].shape);' % (ind_ndim, n_views - 1))
+    else:
+        lines.append('  CIndexer<%d> _ind(_p.size, _p.shape);' % (ndim if spec.uses_ind else 1))
     lines.append('  ' + spec.loop_prep + ';')
     lines.append('  _Tiler _t(_p, _tm);' if tma else '  _Tiler _t(_p);')
     lines.append('  auto _tile = [&](auto _full_tag) {')

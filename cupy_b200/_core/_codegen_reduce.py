@@ -95,13 +95,17 @@ def _functor_source(kernel, in_args, in_params, out_args, out_params, type_map, 
     lines.append('struct _Op {')
     lines.append('  typedef _type_reduce acc_t; typedef IndexT index_t; struct ctx_t {};')
     lines.append('  static constexpr bool kWideIndex = false;')
-    in_bind, out_bind, members = [], [], []
+    in_bind, out_bind, members, raw_bind = [], [], [], []
     k_arr = 0
     for a, p in zip(in_args, in_params):
         if isinstance(a, ndarray):
-            if p.raw:
-                raise NotImplementedError('raw arguments of reduction kernels are not supported')
             mem_t = get_typename(a.dtype)
+            if p.raw:
+                # not broadcast, indexed by the user code with _i / _j / _J (cupy/_core/_reduction.pyx:186-225)
+                members.append('  b200::RawView _rv_%s;' % p.name)
+                raw_bind.append('    const CArray<%s, %d, %s, false> %s(_rv_%s);'
+                                % (mem_t, a.ndim, 'true' if a._c_contiguous else 'false', p.name, p.name))
+                continue
             ctype = p.ctype if p.ctype else mem_t
             if kernel_is_simple(kernel):
                 in_bind.append('    const type_in0_raw in0 = *reinterpret_cast<const type_in0_raw*>(_ptrs[%d]);' % k_arr)
@@ -111,6 +115,8 @@ def _functor_source(kernel, in_args, in_params, out_args, out_params, type_map, 
         else:
             members.append('  alignas(8) %s %s;' % (p.ctype, p.name))
     for k, (a, p) in enumerate(zip(out_args, out_params)):
+        if p.raw:
+            raise NotImplementedError('raw output arguments of reduction kernels are not supported')
         mem_t = get_typename(a.dtype)
         if kernel_is_simple(kernel):
             out_bind.append('    type_out0_raw& out0 = *reinterpret_cast<type_out0_raw*>(_optrs[%d]);' % k)
@@ -121,13 +127,19 @@ def _functor_source(kernel, in_args, in_params, out_args, out_params, type_map, 
     ident = kernel.identity
     lines.append('  __device__ acc_t identity() const { return _type_reduce(%s); }' % ident)
     lines.append('  __device__ acc_t combine(const acc_t& a, const acc_t& b) const { return (%s); }' % reduce_expr)
-    lines.append('  __device__ acc_t map_at(const char* const* _ptrs, index_t _J) const {')
+    # _i: output index, _J: index along the reduced axes, _j = _i + _J * out_size: the reference's linear
+    # input index when the reduced axes lead (cupy/_core/_reduction.pyx:80-89); generic skeleton only
+    lines.append('  __device__ acc_t map_at(const char* const* _ptrs, index_t _J, ptrdiff_t _i = 0) const {')
     lines.append('    const CSizeIndexer _in_ind = {(ptrdiff_t)_in_size}, _out_ind = {(ptrdiff_t)_out_size};')
+    if raw_bind:
+        lines.append('    const ptrdiff_t _j = _i + (ptrdiff_t)_J * (ptrdiff_t)_out_size; (void)_j;')
+    lines.extend(raw_bind)
     lines.extend(in_bind)
     lines.append('    return static_cast<_type_reduce>(%s);' % map_expr)
     lines.append('  }')
-    lines.append('  __device__ void post_at(char* const* _optrs, const acc_t& a) const {')
+    lines.append('  __device__ void post_at(char* const* _optrs, const acc_t& a, ptrdiff_t _i = 0) const {')
     lines.append('    const CSizeIndexer _in_ind = {(ptrdiff_t)_in_size}, _out_ind = {(ptrdiff_t)_out_size};')
+    lines.extend(raw_bind)
     lines.extend(out_bind)
     lines.append('    %s;' % post_map_expr)
     lines.append('  }')
@@ -160,9 +172,18 @@ def kernel_is_simple(kernel):
     return hasattr(kernel, '_ops')
 
 
-def _pack_op(in_args, n_in, n_out):
+def _pack_raw_view(a):
+    """b200::RawView (csrc/include/b200/carray.cuh): data, size, ndim, pad, shape[10], strides[10]."""
+    pad = [0] * (_lib.MAX_NDIM - a.ndim)
+    return struct.pack('<Qqii%dq%dq' % (_lib.MAX_NDIM, _lib.MAX_NDIM), a.ptr, a.size, a.ndim, 0,
+                       *(list(a.shape) + pad), *(list(a.strides) + pad))
+
+
+def _pack_op(in_args, n_in, n_out, in_params=None):
     b = b''
-    for a in in_args:
+    for k, a in enumerate(in_args):
+        if isinstance(a, ndarray) and in_params is not None and in_params[k].raw:
+            b += _pack_raw_view(a)
         if isinstance(a, CScalar):
             raw = numpy.asarray(a.value, dtype=a.descr).tobytes()
             if len(raw) > 8:
@@ -289,7 +310,13 @@ def _launch(fn, grid, threads, params, stream):
 
 def launch_generic(kernel, in_args, out_args, a_shape, reduce_axis, out_axis, keepdims, in_types, out_types,
                    type_map, map_expr, reduce_expr, post_map_expr, reduce_type, stream):
-    arrays = [a for a in in_args if isinstance(a, ndarray)]
+    raws = [(a, p) for a, p in zip(in_args, kernel.in_params) if isinstance(a, ndarray) and p.raw]
+    arrays = [a for a, p in zip(in_args, kernel.in_params) if isinstance(a, ndarray) and not p.raw]
+    if raws and tuple(reduce_axis) + tuple(out_axis) != tuple(range(len(a_shape))):
+        # same restriction as the reference (_set_permuted_args, cupy/_core/_reduction.pyx:186-203)
+        raise NotImplementedError('Illegal conditions')
+    if not arrays:
+        raise ValueError('Loop size is undecided.')
     nin, nout = len(arrays), len(out_args)
     red_shape = [a_shape[i] for i in reduce_axis if a_shape[i] != 1]
     out_dims = [i for i in out_axis if a_shape[i] != 1]
@@ -333,7 +360,8 @@ def launch_generic(kernel, in_args, out_args, a_shape, reduce_axis, out_axis, ke
     grid = (max(1, min((out_size + per_block - 1) // per_block, _sm_count() * 32)), 1, 1)
     key = ('g', nin, nout, group, index64, tuple(a.dtype.char for a in arrays),
            tuple(o.dtype.char for o in out_args), type_map, reduce_type,
-           tuple(a.descr.char for a in in_args if isinstance(a, CScalar)))
+           tuple(a.descr.char for a in in_args if isinstance(a, CScalar)),
+           tuple((a.dtype.char, a.ndim, a._c_contiguous) for a, _ in raws))
     fn = kernel._memo.get(key)
     name = kernel.name + '_generic_g%d' % group
     if fn is None:
@@ -348,5 +376,5 @@ extern "C" __global__ void __launch_bounds__(%d) %s(const __grid_constant__ _Par
         kernel._cached_codes.setdefault(tuple(a.dtype.char for a in arrays), src)
         fn = _jit.get_function(src, name, tuple(kernel.options))
         kernel._memo[key] = fn
-    params = _pack_op(in_args, red_size * out_size, out_size) + blob
+    params = _pack_op(in_args, red_size * out_size, out_size, kernel.in_params) + blob
     _launch(fn, grid, _THREADS, params, stream)

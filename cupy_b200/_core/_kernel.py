@@ -342,8 +342,9 @@ tunables = {
 }
 
 
-def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stream=None):
-    """spec: _codegen.EwSpec describing parameters / operation strings."""
+def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stream=None, ind_shape=None):
+    """spec: _codegen.EwSpec describing parameters / operation strings.  `ind_shape`: the un-collapsed loop
+    shape `_ind` must present (reduce_dims=False kernels that read `_ind`), else None."""
     variant = plan.variant
     threads = tunables['threads'] if block_size is None else int(block_size)
     if variant == _lib.EW_TILED:
@@ -401,12 +402,14 @@ def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stre
                 regs_in += regs
         est = max(regs_in, regs_out) + (64 if esz == 2 else 30)
         min_blocks = tunables['reg_min_blocks'] or max(1, min(3 if n_arrays <= 2 else 5, 65536 // (256 * est)))
-    key = (name, variant, vec, unroll, threads, bool(plan.idx32), plan.ndim if spec.uses_ind else -1, arginfo, access, min_blocks)
+    ind_ndim = len(ind_shape) if (ind_shape is not None and spec.uses_ind) else 0
+    key = (name, variant, vec, unroll, threads, bool(plan.idx32), plan.ndim if spec.uses_ind else -1, arginfo, access,
+           min_blocks, ind_ndim)
     fn = spec.memo.get(key)
     if fn is None:
         source = _codegen.render_elementwise(
             spec, name, args, params, variant=variant, vec=vec, unroll=unroll, threads=threads,
-            idx32=bool(plan.idx32), ndim=plan.ndim, access_spec=access, min_blocks=min_blocks)
+            idx32=bool(plan.idx32), ndim=plan.ndim, access_spec=access, min_blocks=min_blocks, ind_ndim=ind_ndim)
         spec.last_source = source
         fn = _jit.get_function(source, name, spec.options)
         spec.memo[key] = fn
@@ -417,7 +420,11 @@ def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stre
                        shape=tuple(plan.shape[:plan.ndim]), source=spec.last_source)
         return
     st = current_stream_ptr() if stream is None else _stream_ptr(stream)
-    _lib.check(_lib.lib.b200_jit_ew_launch(fn.handle, ctypes.byref(plan), len(args), ops, threads, st))
+    if ind_ndim:
+        shp = (ctypes.c_int64 * ind_ndim)(*ind_shape)
+        _lib.check(_lib.lib.b200_jit_ew_launch_ex(fn.handle, ctypes.byref(plan), len(args), ops, threads, ind_ndim, shp, st))
+    else:
+        _lib.check(_lib.lib.b200_jit_ew_launch_ex(fn.handle, ctypes.byref(plan), len(args), ops, threads, 0, None, st))
 
 
 def _stream_ptr(stream):
@@ -522,8 +529,11 @@ class ElementwiseKernel:
         # the tilers are built for 256 -- a caller's explicit block_size is honoured
         bs = None if block_size == 128 else block_size
         self._spec.type_map = type_map
+        # reduce_dims=False: `_ind` presents the un-collapsed loop shape (cupy/_core/_kernel.pyx:926-929);
+        # the operands are still collapsed for addressing -- only the indexer keeps the original rank
         _launch_jit(self.name, self._spec.bind(type_map), inout_args, self.params, self.nin, ops, plan,
-                    block_size=bs, stream=stream)
+                    block_size=bs, stream=stream,
+                    ind_shape=None if (self.reduce_dims or len(shape) == 0) else tuple(shape))
         key = tuple(t for t in in_ndarray_types if t is not None)
         if key not in self._cached_codes:
             self._cached_codes[key] = self._spec.bind(type_map).last_source

@@ -38,6 +38,7 @@ class _Var:
         self.ndim = ndim
         self.weak_t = weak_t
         self.param_index = param_index
+        self.param_name = name if param_index is not None else None   # `name` follows in-place updates
         self.reduced = False
 
     # ---- the subset of the ndarray surface a fused function may touch
@@ -165,9 +166,10 @@ class _Trace:
                                 % (value.dtype, target.dtype))
             value = self.cast(value, target.dtype)
         self.assigned[target.param_index] = value
-        # later reads of the parameter see the new value
-        alias = _Var(self, value.name, target.dtype, True, target.ndim, param_index=target.param_index)
-        return alias
+        # every reference to the parameter (the user's own variable included: `cp.add(a, b, out=a); a * 2`)
+        # reads the new value from here on, as with a real array
+        target.name = value.name
+        return target
 
     # ---- recorded calls
     def call_ufunc(self, uf, *args, **kwargs):
@@ -267,7 +269,7 @@ class _FusedKernel:
         for r in rets:
             if not isinstance(r, _Var):
                 raise TypeError('a fused function must return values computed from its arguments (got %r)' % (r,))
-        in_decl = ', '.join('%s %s' % (p.dtype.name, p.name) for p in trace.params)   # parameter types are NumPy names
+        in_decl = ', '.join('%s %s' % (p.dtype.name, p.param_name) for p in trace.params)   # parameter types are NumPy names
         preamble = '\n'.join(trace.preambles)
         body = '\n'.join(trace.steps)
         self.inplace = sorted(trace.assigned.items())
@@ -287,7 +289,7 @@ class _FusedKernel:
             stores.append('_o%d = %s;' % (k, r.name))
         for k, (pidx, v) in enumerate(self.inplace):
             out_decl.append('%s _w%d' % (trace.params[pidx].dtype.name, k))
-            stores.append('_w%d = %s;' % (k, v.name))
+            stores.append('_w%d = %s;' % (k, trace.params[pidx].name))
         if not out_decl:
             raise ValueError('the fused function neither returns nor updates an array')
         self.n_ret = len(outs)
@@ -313,8 +315,8 @@ class _FusedKernel:
         out_t = op.out_types[0]
         if reduce_type is None:
             reduce_type = get_typename(out_t)
-        args_decl = ', '.join('const %s& %s' % (get_typename(p.dtype), p.name) for p in trace.params)
-        args_call = ', '.join(p.name for p in trace.params)
+        args_decl = ', '.join('const %s& %s' % (get_typename(p.dtype), p.param_name) for p in trace.params)
+        args_call = ', '.join(p.param_name for p in trace.params)
         pre = [preamble, kernel.preamble,
                'typedef %s type_in0_raw;' % get_typename(a.dtype),
                'typedef %s type_out0_raw;' % get_typename(out_t),

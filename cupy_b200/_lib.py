@@ -124,6 +124,8 @@ _EXPORTS = {
     'b200_module_unload': (c_int, [c_void_p]),
     'b200_module_get_function': (c_int, [c_void_p, c_char_p, POINTER(c_void_p)]),
     'b200_jit_ew_launch': (c_int, [c_void_p, POINTER(EwPlan), c_int, POINTER(Operand), c_int, c_void_p]),
+    'b200_jit_ew_launch_ex': (c_int, [c_void_p, POINTER(EwPlan), c_int, POINTER(Operand), c_int, c_int, POINTER(c_int64),
+                                     c_void_p]),
     'b200_jit_launch': (c_int, [c_void_p, c_uint, c_uint, c_uint, c_uint, c_uint, c_void_p, c_size_t, c_void_p]),
 }
 

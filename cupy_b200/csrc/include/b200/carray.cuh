@@ -18,8 +18,11 @@ struct RawView {
     int64_t strides[kMaxNdim];   // bytes
 };
 
-// up to four `raw` operands per kernel, passed as the second kernel parameter
-struct RawPack { RawView v[4]; };
+// the `raw` operands of a kernel (one view each, in operand order), passed as the second kernel parameter;
+// generated kernels declare exactly as many as they use (+ one trailing shape-only view carrying the
+// un-collapsed loop shape when the user code reads `_ind` of a reduce_dims=False kernel)
+template <int N> struct RawPackN { RawView v[N > 0 ? N : 1]; };
+typedef RawPackN<4> RawPack;
 
 }  // namespace b200
 

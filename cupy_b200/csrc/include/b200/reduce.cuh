@@ -402,15 +402,15 @@ __device__ __forceinline__ void reduce_generic_body(const Op& op, const GenericR
 #pragma unroll
                     for (int a = 0; a < NIN; ++a) ptrs[a] += r * p.in_red_strides[a][d];
                 }
-                acc = op.combine(acc, op.map_at(ptrs, static_cast<index_t>(j)));
+                acc = op.combine(acc, op.map_at(ptrs, static_cast<index_t>(j), static_cast<ptrdiff_t>(o)));
             }
         }
         if (GROUP == THREADS) {
             acc = block_combine(op, acc, smem);
-            if (threadIdx.x == 0) op.post_at(obase, acc);
+            if (threadIdx.x == 0) op.post_at(obase, acc, static_cast<ptrdiff_t>(o));
         } else {
             if (GROUP > 1) acc = group_combine<(GROUP > 32 ? 32 : GROUP)>(op, acc);
-            if (g == 0 && live) op.post_at(obase, acc);
+            if (g == 0 && live) op.post_at(obase, acc, static_cast<ptrdiff_t>(o));
         }
     }
 }

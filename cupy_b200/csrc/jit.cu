@@ -205,19 +205,26 @@ extern "C" __attribute__((visibility("default"))) int b200_jit_launch(void* func
 
 extern "C" __attribute__((visibility("default"))) int b200_jit_ew_launch(void* function, const b200_ew_plan_t* plan, int nargs,
                                   const b200_operand_t* args, int block_size, void* stream) {
+    return b200_jit_ew_launch_ex(function, plan, nargs, args, block_size, 0, nullptr, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int b200_jit_ew_launch_ex(void* function, const b200_ew_plan_t* plan, int nargs,
+                                  const b200_operand_t* args, int block_size, int ind_ndim, const int64_t* ind_shape,
+                                  void* stream) {
     if (!function || !plan || !args) return fail(B200_E_INVALID, "null argument");
+    if (ind_ndim < 0 || ind_ndim > kMaxNdim || (ind_ndim > 0 && !ind_shape)) return fail(B200_E_INVALID, "bad ind_ndim");
     if (plan->size == 0) return 0;
     Driver* d = driver();
     if (!d) return fail(B200_E_NOLIB, "libcuda could not be loaded");
     EwParams p;
     int st = fill_ew_params(plan, nargs, args, &p);
     if (st) return st;
-    RawPack raws;
+    // the kernel declares RawPackN<n> for exactly the views it uses; the driver copies that many from here
+    RawPackN<kMaxArgs + 1> raws;
     memset(&raws, 0, sizeof(raws));
     int nraw = 0;
     for (int a = 0; a < nargs; ++a) {
         if (args[a].kind != B200_KIND_RAW) continue;
-        if (nraw == 4) return fail(B200_E_UNSUPPORTED, "more than 4 raw array operands");
         if (args[a].ndim > kMaxNdim) return fail(B200_E_UNSUPPORTED, "raw operand rank %d exceeds %d", args[a].ndim, kMaxNdim);
         RawView& v = raws.v[nraw++];
         v.data = static_cast<char*>(args[a].data);
@@ -227,6 +234,15 @@ extern "C" __attribute__((visibility("default"))) int b200_jit_ew_launch(void* f
             v.shape[k] = args[a].shape[k];
             v.strides[k] = args[a].strides[k];
             v.size *= args[a].shape[k];
+        }
+    }
+    if (ind_ndim > 0) {          // shape-only view: the un-collapsed loop shape user code sees through `_ind`
+        RawView& v = raws.v[nraw++];
+        v.ndim = ind_ndim;
+        v.size = 1;
+        for (int k = 0; k < ind_ndim; ++k) {
+            v.shape[k] = ind_shape[k];
+            v.size *= ind_shape[k];
         }
     }
     DeviceInfo di;

@@ -242,10 +242,16 @@ typedef struct b200_raw_view {
 } b200_raw_view_t;
 
 /* Launch an NVRTC-built elementwise kernel generated over the skeleton in
- * cupy_b200/csrc/include/b200/elementwise.cuh.  `orig_ndim/orig_shape` is the
- * un-collapsed loop shape (what user code sees through `_ind`). */
+ * cupy_b200/csrc/include/b200/elementwise.cuh. */
 int b200_jit_ew_launch(void* function, const b200_ew_plan_t* plan, int nargs,
                        const b200_operand_t* args, int block_size, void* stream);
+/* Same; additionally hands the kernel the UN-collapsed loop shape (`ind_ndim`, `ind_shape`) for kernels
+ * created with reduce_dims=False whose code reads `_ind` (the reference builds the Indexer from the original
+ * shape then, cupy/_core/_kernel.pyx:931-940).  ind_ndim = 0: as b200_jit_ew_launch.  Any number of `raw`
+ * operands (<= B200_MAX_ARGS) is accepted. */
+int b200_jit_ew_launch_ex(void* function, const b200_ew_plan_t* plan, int nargs,
+                          const b200_operand_t* args, int block_size, int ind_ndim, const int64_t* ind_shape,
+                          void* stream);
 
 /* Launch an NVRTC-built reduction kernel (skeleton: b200/reduce.cuh).
  * `params` is the packed by-value kernel parameter block built by the host. */

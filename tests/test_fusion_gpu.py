@@ -147,3 +147,18 @@ def test_errors_and_fallbacks(cp):
     outside = cp.asarray(rnd((10,)))
     with pytest.raises(TypeError):
         cp.fuse(lambda x: x + outside)(cp.asarray(rnd((10,))))
+
+
+def test_out_argument_then_read(cp):
+    """`cp.add(a, b, out=a); return a * 2` computes (a + b) * 2 and updates a."""
+    @cp.fuse(kernel_name='fused_out_read')
+    def f(a, b):
+        cp.add(a, b, out=a)
+        return a * 2
+
+    rs = np.random.RandomState(3)
+    a, b = rs.rand(1000).astype('f'), rs.rand(1000).astype('f')
+    da, db = cp.asarray(a), cp.asarray(b)
+    r = f(da, db)
+    np.testing.assert_array_equal(r.get(), (a + b) * 2)
+    np.testing.assert_array_equal(da.get(), a + b)

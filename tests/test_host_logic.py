@@ -340,12 +340,16 @@ def test_codegen_skips_the_load_of_write_first_outputs(dry):
     from cupy_b200._core._codegen import writes_first as w
     assert w('z = exp(x) + v', 'z') and w('z = a * x + y', 'z') and w('z = x > 0 ? x : 0', 'z')
     assert w('T t = x * 2; z = t; w = z + 1', 'z') and w('T t = x * 2; z = t; w = z + 1', 'w')
-    for op in ('z += x', 'y = z; z = x', 'if (x > 0) z = x', 'z == x', 'zz = 1', 'for (int k = 0; k < 2; ++k) { z = x; }'):
+    for op in ('z += x', 'y = z; z = x', 'if (x > 0) z = x', 'z == x', 'zz = 1', 'for (int k = 0; k < 2; ++k) { z = x; }',
+               'z = z + x', 'z = c ? x : z', 'T t = x; z = t * z'):      # read-modify-write through the right-hand side
         assert not w(op, 'z'), op
+    assert w('z = x; z = z + 1', 'z')          # reads the value the kernel itself wrote
     x = cp.empty((1 << 16,), 'f')
     cp.ElementwiseKernel('T x', 'T z', 'z = x * 2', 'wf_a')(x)
     assert 'load<_FULL>(1' not in dry[-1]['source']
     cp.ElementwiseKernel('T x', 'T z', 'z += x', 'wf_b')(x, cp.empty((1 << 16,), 'f'))
+    assert 'load<_FULL>(1' in dry[-1]['source']
+    cp.ElementwiseKernel('T x', 'T z', 'z = z + x', 'wf_c')(x, cp.empty((1 << 16,), 'f'))
     assert 'load<_FULL>(1' in dry[-1]['source']
 
 
@@ -372,6 +376,53 @@ def test_fuse_traces_into_one_kernel(dry):
         cp.fuse(lambda x: cp.sum(x) * 2)(cp.empty((8,), 'f'))
     with pytest.raises(TypeError):
         cp.fuse(lambda x: x if x > 0 else x)(cp.empty((8,), 'f'))
+
+
+def test_reduce_dims_false_keeps_the_indexer_rank_and_raw_operands_are_uncapped(dry):
+    # a reduce_dims=False kernel reading _ind.get()[k] must see the ORIGINAL loop shape
+    k = cp.ElementwiseKernel('T x', 'int64 r, int64 c', 'r = _ind.get()[0]; c = _ind.get()[1]', 'ind2d', reduce_dims=False)
+    k(cp.empty((4, 6), 'f'))
+    src = dry[-1]['source']
+    assert 'CIndexer<2> _ind(_p.size, _rv.v[0].shape)' in src and 'RawPackN<1>' in src
+    assert dry[-1]['ndim'] == 1                            # the operands themselves still collapse
+    k1 = cp.ElementwiseKernel('T x', 'int64 r', 'r = _ind.get()[0]', 'ind_collapsed')      # reduce_dims=True: collapsed
+    k1(cp.empty((4, 6), 'f'))
+    assert 'CIndexer<1> _ind(_p.size, _p.shape)' in dry[-1]['source']
+    # more than four raw operands (the round-1 cap)
+    names = ['a', 'b', 'c', 'd', 'e', 'f']
+    k6 = cp.ElementwiseKernel(', '.join('raw T %s' % n for n in names), 'T z',
+                              'z = ' + ' + '.join('%s[i]' % n for n in names), 'six_raw')
+    k6(*[cp.empty((32,), 'f') for _ in names], size=32)
+    assert 'RawPackN<6>' in dry[-1]['source']
+
+
+def test_reduction_kernel_accepts_raw_inputs(dry):
+    # `raw` in-params (cupy/_core/_reduction.pyx:186-225, 886-900): not broadcast, indexed by user code
+    k = cp.ReductionKernel('T x, raw T w', 'T y', 'x * w[_j % 5]', 'a + b', 'y = a', '0', 'raw_weights')
+    r = k(cp.empty((7, 5), 'f'), cp.empty((5,), 'f'), axis=0)
+    assert r.shape == (5,) and 'generic' in dry[-1]['name']
+    src = k.cached_code
+    assert 'b200::RawView _rv_w;' in src and 'CArray<float, 1, true, false> w(_rv_w);' in src
+    with pytest.raises(NotImplementedError):          # the reduced axes must lead when raw arguments are used
+        k(cp.empty((7, 5), 'f'), cp.empty((5,), 'f'), axis=1)
+
+
+def test_fuse_out_argument_updates_every_reference_to_the_parameter(dry):
+    # cp.add(a, b, out=a) followed by a read of `a` must see a + b (NumPy / reference semantics), not the old a
+    @cp.fuse(kernel_name='fused_out_then_read')
+    def f(a, b):
+        cp.add(a, b, out=a)
+        return a * 2
+
+    f(cp.empty((64,), 'f'), cp.empty((64,), 'f'))
+    src = dry[-1]['source']
+    import re
+    mul = src[src.index('out0 = in0 * in1'):]
+    before_mul = src[:src.index('out0 = in0 * in1')]
+    # the multiply reads the temporary holding a + b, never parameter _p0 again
+    last_in0 = re.findall(r'const in0_type in0 = static_cast<in0_type>\((\w+)\);', before_mul)[-1]
+    assert last_in0.startswith('_t'), last_in0
+    assert '_w0 = _t' in mul
 
 
 def test_fused_and_user_reductions_use_the_structured_skeletons(dry):
