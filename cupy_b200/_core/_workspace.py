@@ -26,11 +26,25 @@ def get(nbytes, stream_ptr):
     if buf is None or buf.numel() < nbytes:
         size = max(nbytes, 1 << 20)
         size = (size + 255) // 256 * 256
-        # a fresh buffer replaces the old one; kernels in flight on this stream keep
-        # using the old allocation, which the caching allocator only reuses in stream order
-        buf = torch.zeros(size, dtype=torch.uint8, device='cuda')
+        # The buffer belongs to the stream the kernels run on, not to torch's current stream: it is
+        # allocated under that stream (so the caching allocator reuses a replaced buffer only in THAT
+        # stream's order -- kernels still in flight on it keep their old allocation intact) and zeroed
+        # by a memset enqueued on that stream, ahead of the first kernel that reads the tickets.
+        with torch.cuda.stream(_as_torch_stream(stream_ptr)):
+            buf = torch.empty(size, dtype=torch.uint8, device='cuda')
+        from cupy_b200 import _lib
+        _lib.check(_lib.lib.b200_workspace_init(buf.data_ptr(), size, stream_ptr))
         _pool[key] = buf
     return buf.data_ptr(), buf.numel()
+
+
+def _as_torch_stream(stream_ptr):
+    cur = torch.cuda.current_stream()
+    if cur.cuda_stream == stream_ptr:
+        return cur
+    if stream_ptr == 0:
+        return torch.cuda.default_stream()
+    return torch.cuda.ExternalStream(stream_ptr)
 
 
 def clear():

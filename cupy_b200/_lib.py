@@ -103,6 +103,7 @@ _EXPORTS = {
     'b200_last_error_string': (c_char_p, []),
     'b200_device_info': (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
     'b200_dtype_itemsize': (c_int, [c_int]),
+    'b200_workspace_init': (c_int, [c_void_p, c_size_t, c_void_p]),
     'b200_ew_plan': (c_int, [c_int, POINTER(Operand), POINTER(EwPlan)]),
     'b200_ew_plan_ex': (c_int, [c_int, POINTER(Operand), c_uint32, POINTER(EwPlan)]),
     'b200_ufunc_supported': (c_int, [c_int, c_int, POINTER(c_int32), c_int32]),

@@ -169,7 +169,9 @@ __device__ __forceinline__ void reduce_full_body(
     if (threadIdx.x == 0) {
         partials[blockIdx.x] = r;
         __threadfence();
-        const uint32_t t = atomicAdd(ticket, 1u);
+        // self-resetting ticket: atomicInc wraps to 0 on the last arrival, so the workspace is left zeroed
+        // without a separate store (one launch = exactly gridDim.x arrivals)
+        const uint32_t t = atomicInc(ticket, gridDim.x - 1);
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
@@ -179,10 +181,7 @@ __device__ __forceinline__ void reduce_full_body(
     for (int i = threadIdx.x; i < int(gridDim.x); i += THREADS)
         r = op.combine(r, load_volatile(partials + i));
     r = block_combine(op, r, smem);
-    if (threadIdx.x == 0) {
-        y[0] = op.post(r, n);
-        *ticket = 0u;
-    }
+    if (threadIdx.x == 0) y[0] = op.post(r, n);
 }
 
 // ---------------------------------------------------------------------------
@@ -320,7 +319,7 @@ __device__ __forceinline__ void reduce_cols_body(
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t t = atomicAdd(&tickets[b * gridDim.x + blockIdx.x], 1u);
+        const uint32_t t = atomicInc(&tickets[b * gridDim.x + blockIdx.x], uint32_t(nsplit) - 1);   // self-resetting
         is_last = (t == uint32_t(nsplit) - 1);
     }
     __syncthreads();
@@ -333,7 +332,6 @@ __device__ __forceinline__ void reduce_cols_body(
             a = op.combine(a, load_volatile(partials + (b * nsplit + s) * cols + tile_c0 + t));
         y[b * cols + tile_c0 + t] = op.post(a, n);
     }
-    if (threadIdx.x == 0) tickets[b * gridDim.x + blockIdx.x] = 0u;
 }
 
 // ---------------------------------------------------------------------------

@@ -211,6 +211,12 @@ extern "C" __attribute__((visibility("default"))) int b200_device_info(int* sm_c
     return 0;
 }
 
+extern "C" __attribute__((visibility("default"))) int b200_workspace_init(void* workspace, size_t bytes, void* stream) {
+    if (!workspace && bytes) return fail(B200_E_INVALID, "null workspace");
+    if (bytes) B200_CUDA_TRY(cudaMemsetAsync(workspace, 0, bytes, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 static int plan_impl(int nargs, const b200_operand_t* args, uint32_t flags, b200_ew_plan_t* plan);
 
 extern "C" __attribute__((visibility("default"))) int b200_ew_plan(int nargs, const b200_operand_t* args, b200_ew_plan_t* plan) {

@@ -142,7 +142,8 @@ static int run(int op, const void* x, void* y, int64_t n, void* wsp, size_t ws_b
         const int st = run_tma<In>(op, x, y, n, wsp, ws_bytes, stream);
         if (st != B200_E_UNSUPPORTED) return st;
     }
-    if (n >= kFlatLinesMinN && getenv("B200_SCAN_LOOKBACK") == nullptr) {
+    static const bool force_lookback = getenv("B200_SCAN_LOOKBACK") != nullptr;     // read once, not per call
+    if (n >= kFlatLinesMinN && !force_lookback) {
         DeviceInfo di;
         int st = device_info(&di);
         if (st) return st;

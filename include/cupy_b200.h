@@ -166,6 +166,12 @@ const char* b200_last_error_string(void);
 int         b200_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
 int         b200_dtype_itemsize(int dtype);
 
+/* Zero-fills a freshly allocated reduction / scan workspace ON `stream` (cudaMemsetAsync), i.e. ordered before
+ * the kernels the caller enqueues on that stream afterwards.  Workspaces must be initialised this way once; the
+ * kernels leave them zeroed (self-resetting tickets), so a workspace is reused without further memsets as
+ * long as it is used on ONE stream at a time. */
+int b200_workspace_init(void* workspace, size_t bytes, void* stream);
+
 /* ---- elementwise launcher */
 int b200_ew_plan(int nargs, const b200_operand_t* args, b200_ew_plan_t* plan);
 /* Same, with flags.  B200_PLAN_KEEP_ORDER: the kernel observes the C-order linear index (`i`, `_ind`, raw

@@ -680,3 +680,39 @@ def test_reduction_kernel_raw_inputs(cp):
     got = k2(cp.asarray(x), cp.asarray(flat), cp.asarray(bias[:3]), axis=(0, 1)).get()
     want = (x.astype(np.float64) + flat.reshape(37, 5, 3) + bias[:3]).sum(axis=(0, 1))
     np.testing.assert_allclose(got, want, rtol=1e-5)
+
+
+def test_reductions_on_a_non_current_stream_while_another_stream_is_busy(cp):
+    """workspaces (tickets) are zeroed and owned by the stream the kernel runs on, not by
+    torch's current stream: first use of `stream=` on a fresh, non-current stream while the current stream
+    is kept busy must still see zeroed tickets (full reductions and split COLS reductions)."""
+    import torch
+    from cupy_b200._core import _workspace
+    _workspace.clear()
+    rs = np.random.RandomState(21)
+    a = rs.rand(1 << 20).astype(np.float32)
+    m = rs.rand(4096, 64).astype(np.float32)          # few columns: COLS split along the reduced axis (tickets)
+    da, dm = cp.asarray(a), cp.asarray(m)
+    busy = cp.asarray(rs.rand(1 << 24).astype(np.float32))
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    k = cp.ReductionKernel('T x', 'T y', 'x', 'a + b', 'y = a', '0', 'sum_on_stream')
+    for _ in range(20):                               # keep the CURRENT stream busy
+        busy = busy * 1.0001
+    s1 = k(da, stream=side)                           # JIT reduction, FULL layout, tickets on `side`
+    s0 = k(dm, axis=0, stream=side)                   # split COLS
+    side.synchronize()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(s1.get(), a.astype(np.float64).sum(), rtol=1e-5)
+    np.testing.assert_allclose(s0.get(), m.astype(np.float64).sum(axis=0), rtol=1e-5)
+    # and again (the tickets were left zeroed by the kernels themselves)
+    s1 = k(da, stream=side)
+    side.synchronize()
+    np.testing.assert_allclose(s1.get(), a.astype(np.float64).sum(), rtol=1e-5)
+    # prebuilt reductions under `with stream:`
+    with cp.cuda.Stream(non_blocking=True) as st2:
+        r = da.sum()
+        c = dm.sum(axis=0)
+        st2.synchronize()
+    np.testing.assert_allclose(r.get(), a.astype(np.float64).sum(), rtol=1e-5)
+    np.testing.assert_allclose(c.get(), m.astype(np.float64).sum(axis=0), rtol=1e-5)
