@@ -26,6 +26,9 @@ from cupy_b200._core._routines_more import (  # noqa: F401,E402
 from cupy_b200 import cuda  # noqa: F401,E402
 from cupy_b200._core.fusion import fuse  # noqa: F401,E402
 
+from cupy_b200._core._accelerator import (  # noqa: F401,E402
+    set_routine_accelerators, set_reduction_accelerators, get_routine_accelerators, get_reduction_accelerators)
+
 abs = absolute
 max = amax
 min = amin

@@ -872,6 +872,8 @@ class ufunc:
             return array.sum(axis, dtype, out, keepdims)
         if self.name == 'cupy_multiply':
             return array.prod(axis, dtype, out, keepdims)
+        if self.name in ('cupy_maximum', 'cupy_minimum') and dtype is None:
+            return (array.max if self.name == 'cupy_maximum' else array.min)(axis, out, keepdims)
         raise NotImplementedError('`%s.reduce` is not supported yet' % self.name)
 
     def accumulate(self, array, axis=0, dtype=None, out=None):

@@ -537,6 +537,51 @@ class ndarray:
         raise TypeError('Implicit conversion to a NumPy array is not allowed. '
                         'Please use `.get()` to construct a NumPy array explicitly.')
 
+    # ---- NumPy dispatch protocols (cupy/_core/core.pyx:1969-2037) ------------------------
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        """`numpy.multiply(x, 2)` on a device array runs the engine's ufunc of the same name.  Host
+        numpy.ndarray operands are not converted silently: the ufunc raises TypeError, as in the
+        reference."""
+        import cupy_b200
+        inout = inputs
+        if 'out' in kwargs:
+            out = kwargs['out']
+            if not isinstance(out, tuple):
+                out = (out,)
+            if len(out) != 1:
+                raise ValueError('The \'out\' parameter must have exactly one array value')
+            inout += out
+            kwargs['out'] = out[0]
+        if method not in ('__call__', 'outer', 'at', 'reduce', 'accumulate', 'reduceat'):
+            return NotImplemented
+        name = ufunc.__name__
+        func = getattr(cupy_b200, name, None)
+        from cupy_b200._core._kernel import ufunc as _ufunc_class
+        if not isinstance(func, _ufunc_class):
+            return NotImplemented
+        if method != '__call__':
+            func = getattr(func, method)
+        for x in inout:
+            if not (isinstance(x, (ndarray, numpy.ndarray, numpy.generic, int, float, bool, complex))
+                    or hasattr(x, '__cuda_array_interface__')):
+                return NotImplemented
+        if name in ('greater', 'greater_equal', 'less', 'less_equal', 'equal', 'not_equal'):
+            # workaround for numpy/numpy#12142 (0-d host arrays in comparisons)
+            inputs = tuple(x.item() if isinstance(x, numpy.ndarray) and x.ndim == 0 else x for x in inputs)
+        return func(*inputs, **kwargs)
+
+    def __array_function__(self, func, types, args, kwargs):
+        """`numpy.sum(x, axis=0)`, `numpy.cumsum(x)` ... -> the cupy_b200 function of the same name."""
+        import cupy_b200
+        if (func.__module__ or '').split('.')[0] != 'numpy' or len((func.__module__ or '').split('.')) > 2:
+            return NotImplemented
+        mine = getattr(cupy_b200, func.__name__, None)
+        if mine is None or mine is func or not callable(mine):
+            return NotImplemented
+        if not all(issubclass(t, (ndarray, numpy.ndarray, numpy.generic, int, float, bool)) for t in types):
+            return NotImplemented
+        return mine(*args, **kwargs)
+
     # ---- arithmetic (cupy/_core/core.pyx:1560-1700) ----------------------------------
     def _binop(self, name, other, reflected=False):
         from cupy_b200._core import _routines_math as m

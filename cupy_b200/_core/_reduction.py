@@ -24,7 +24,7 @@ import ctypes
 import numpy
 
 from cupy_b200 import _lib
-from cupy_b200._core import _codegen_reduce, _dryrun, _jit, _kernel, _scalar, _workspace
+from cupy_b200._core import _accelerator, _codegen_reduce, _dryrun, _jit, _kernel, _scalar, _workspace
 from cupy_b200._core._kernel import (ParameterInfo, _broadcast, _decide_params_type_core,
                                      _get_param_info, _preprocess_args, _stream_ptr)
 from cupy_b200._core._ndarray import ndarray, normalize_axis_index, current_stream_ptr
@@ -209,6 +209,7 @@ class _AbstractReductionKernel:
         layout = Layout(-1, 1, n_reduce, n_out)
         kinds = None
         plain = (len(arrays) >= 1 and len(out_args) == 1 and n_reduce > 0
+                 and _accelerator.fast_paths_enabled()
                  and not any(p.raw for p in self.in_params + self.out_params))
         if plain:
             x0 = next((a for a in arrays if 0 not in [t for t, n_ in zip(a.strides, a.shape) if n_ > 1]), None)
@@ -303,6 +304,10 @@ class _SimpleReductionKernel(_AbstractReductionKernel):
             raise TypeError("Argument 'a' has incorrect type (expected cupy.ndarray, got %s)" % type(a).__name__)
         if out is not None and not isinstance(out, ndarray):
             raise TypeError('Output arguments type must be cupy.ndarray')
+        if _accelerator.reference_first():
+            r = _accelerator.try_reference('reduction', self.name, arr, axis=axis, dtype=dtype, out=out, keepdims=keepdims)
+            if r is not None:
+                return r
         out_args = [] if out is None else [out]
         return self._call([arr], out_args, arr.shape, axis, dtype, keepdims, True, None)
 

@@ -243,6 +243,12 @@ def _scan_flat(src, dst, op):
 def scan_core(a, axis, op, dtype=None, out=None):
     """cupy/_core/_routines_math.pyx:702-751 (dtype rules :704-714)."""
     a = _as_array(a)
+    from cupy_b200._core import _accelerator
+    if _accelerator.reference_first(routine=True):
+        r = _accelerator.try_reference('scan', 'cumsum' if op == _lib.OP_CUMSUM else 'cumprod', a,
+                                       axis=axis, dtype=dtype, out=out)
+        if r is not None:
+            return r
     if out is None:
         if dtype is None:
             kind = a.dtype.kind

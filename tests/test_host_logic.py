@@ -476,3 +476,41 @@ def test_prebuilt_kernels_serve_only_fixed_operand_kinds(dry):
     assert dry[-1]['kind'] == 'prebuilt_ufunc' and dry[-1]['variant'] == _lib.EW_ROWWISE
     cp.add(pad, cp.empty((64, 1), 'f'))                      # column broadcast: specialised
     assert dry[-1]['kind'] == 'jit_elementwise' and 'RowTiler' in dry[-1]['source']
+
+
+def test_accelerator_switch_and_numpy_dispatch(dry):
+    """CUPY_ACCELERATORS-style switch (cupy/_core/_accelerator.pyx) and NumPy's dispatch
+    protocols on the array (cupy/_core/core.pyx:1969-2037)."""
+    from cupy_b200._core import _accelerator
+    assert cp.get_reduction_accelerators() == ['b200']
+    x = cp.empty((64, 128), 'f')
+    x.sum(axis=1)
+    assert dry[-1]['kind'] == 'prebuilt_reduce'
+    cp.set_reduction_accelerators(['generic'])
+    try:
+        x.sum(axis=1)
+        assert dry[-1]['kind'] == 'jit_reduce' and 'generic' in dry[-1]['name']
+        cp.set_reduction_accelerators(['reference'])
+        with pytest.raises(RuntimeError):                  # nothing registered: the package has no oracle
+            x.sum(axis=1)
+        seen = []
+        _accelerator.register_reference_backend(lambda kind, name, a, **kw: seen.append((kind, name)) or None)
+        x.sum(axis=1)                                       # backend declined (None): falls through to the engine
+        assert seen == [('reduction', 'cupy_sum')]
+        with pytest.raises(ValueError):
+            cp.set_reduction_accelerators(['nope'])
+        cp.set_reduction_accelerators('cub')                # the reference's names are accepted
+        assert cp.get_reduction_accelerators() == ['b200']
+    finally:
+        _accelerator.register_reference_backend(None)
+        cp.set_reduction_accelerators(['b200'])
+    # numpy.multiply(x, 2) / numpy.sum(x, axis=0) on a device array reach the engine
+    del dry[:]
+    r = np.multiply(x, 2)
+    assert isinstance(r, cp.ndarray) and r.shape == x.shape and len(dry) == 1
+    r = np.sum(x, axis=0)
+    assert isinstance(r, cp.ndarray) and r.shape == (128,)
+    r = np.add.reduce(x, axis=1)
+    assert isinstance(r, cp.ndarray) and r.shape == (64,)
+    with pytest.raises(TypeError):
+        np.add(x, np.ones((64, 128), 'f'))                  # no silent host-to-device conversion

@@ -100,3 +100,36 @@ def test_cumsum_int64_bit_exact_vs_reference_cub(ref, cp):
     ref.ref_cub_scan(ws.data_ptr(), wsb, yf.data_ptr(), yf.data_ptr(), 1 << 20, stream(), _lib.OP_CUMSUM, _lib.TYPE_FLOAT32)
     of = cp.cumsum(cp.from_torch(tf)).to_torch()
     assert float(((of - yf).abs() / yf).max().item()) <= 1e-5
+
+
+def test_accelerator_switch_routes_whole_calls_through_the_reference_in_tests(ref, cp):
+    """SURVEY section 5 / VERDICT r1 #7: one setter switches a call between the new engine and the reference
+    oracle.  The backend is registered HERE (test infrastructure); the package itself has none."""
+    from cupy_b200._core import _accelerator
+    g = torch.Generator(device='cuda').manual_seed(5)
+    t = torch.rand(1 << 22, device='cuda', generator=g) * 2 - 1
+    x = cp.from_torch(t)
+    calls = []
+
+    def backend(kind, name, a, axis=None, dtype=None, out=None, keepdims=False):
+        if kind != 'reduction' or name != 'cupy_sum' or axis is not None or a.dtype != np.float32:
+            return None
+        y = cp.empty((), np.float32)
+        wsb = ref.ref_cub_reduce_workspace(a.ptr, y.ptr, a.size, stream(), _lib.OP_SUM, _lib.TYPE_FLOAT32)
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device='cuda')
+        ref.ref_cub_reduce(ws.data_ptr(), wsb, a.ptr, y.ptr, a.size, stream(), _lib.OP_SUM, _lib.TYPE_FLOAT32)
+        torch.cuda.synchronize()
+        calls.append(name)
+        return y
+
+    ours = float(x.sum().get())
+    _accelerator.register_reference_backend(backend)
+    cp.set_reduction_accelerators(['reference', 'b200'])
+    try:
+        theirs = float(x.sum().get())
+        assert calls == ['cupy_sum']
+        assert float(x.max().get()) == float(t.max())          # declined by the backend: the engine runs
+    finally:
+        _accelerator.register_reference_backend(None)
+        cp.set_reduction_accelerators(['b200'])
+    assert abs(ours - theirs) <= 1e-5 * float(t.abs().sum())
