@@ -195,11 +195,20 @@ def run_ours(args):
     s = cp.empty((), np.float32)
     axpy = cp.ElementwiseKernel('T a, T x, T y', 'T z', 'z = a * x + y', 'axpy')
 
+    # N > 1: the partial sums are combined across the GPUs inside the reduction kernel's last block, through
+    # NVLink peer memory (cupy_b200.distributed.sharded_sum -> b200_reduce_run_sharded); if the box cannot map
+    # peer memory, sharded_sum falls back to one NCCL all-reduce of the 0-d partial
+    fused = bool(comm is not None and comm.peer_exchange() is not None)
+
+    def reduce_step():
+        if comm is None:
+            x.sum(out=s)
+        else:
+            cdist.sharded_sum(x, comm, out=s)
+
     def step():
         axpy(A, x, y, z)
-        x.sum(out=s)
-        if comm is not None:
-            comm.all_reduce(s, s, 'sum')
+        reduce_step()
 
     def barrier():
         if world > 1:
@@ -223,10 +232,8 @@ def run_ours(args):
         ev_a0[i].record()
         axpy(A, x, y, z)
         ev_a1[i].record()
-        x.sum(out=s)
+        reduce_step()
         ev_s1[i].record()
-        if comm is not None:
-            comm.all_reduce(s, s, 'sum')
     end.record()
     barrier()
     clocks = sampler.result()
@@ -318,7 +325,10 @@ def run_ours(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {
                 'workload': 'ElementwiseKernel axpy z=a*x+y (12 B/elem) + full sum (4 B/elem), float32, '
-                            '2^28 elements per GPU' + ('; partial sums all-reduced over NCCL' if world > 1 else ''),
+                            '2^28 elements per GPU' + (
+                                '' if world == 1 else
+                                '; partial sums combined across GPUs inside the reduction kernel over NVLink peer memory'
+                                if fused else '; partial sums all-reduced over NCCL'),
                 'elements_per_gpu': N_ELEMS, 'algorithmic_bytes_per_step_per_gpu': BYTES_STEP,
                 'l2': 'inputs (3 GiB per GPU) exceed the 126 MB L2; no flush needed',
                 'sharding': 'contiguous 1-D shards, one process per GPU' if world > 1 else 'single GPU',

@@ -527,9 +527,12 @@ def run_c5(world, rank, comm, peak, log2_total=32, iters=20):
     want_var = float(ref[2] / ref[0] - mean * mean)
 
     class Solo:
+        _n_devices, rank = 1, 0
+
         def all_reduce(self, a, b, op='sum', stream=None):
             pass
     c = comm if comm is not None else Solo()
+    fused = bool(comm is not None and comm.peer_exchange() is not None)
     out = {}
     for name, f, want in (('sum', lambda: cdist.sharded_sum(x, c), want_sum),
                           ('var', lambda: cdist.sharded_var(x, c), want_var)):
@@ -557,6 +560,9 @@ def run_c5(world, rank, comm, peak, log2_total=32, iters=20):
                      'frac_per_gpu': round(4 * n_total / ms / 1e6 / world / peak, 4),
                      'check': ('ok' if rel <= 1e-5 else 'MISMATCH') + ' rel_err=%.1e vs float64 (tol 1e-5)' % rel,
                      'identical_on_all_ranks': bool(float(lo_) == float(hi_))}
+    out['combine'] = ('fused: per-GPU partials exchanged through NVLink peer memory inside the reduction kernel '
+                      '(b200_reduce_run_sharded), one launch per GPU' if fused else
+                      'single GPU' if world == 1 else 'NCCL all-reduce / all-gather of the partials (fallback route)')
     out['elements_total'] = n_total
     out['elements_per_gpu'] = n
     out['scaling'] = 'strong (2^%d float32 total, contiguous shards); efficiency = ms(N=1) / (N * ms(N))' % log2_total

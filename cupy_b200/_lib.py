@@ -75,6 +75,15 @@ class ReduceDesc(Structure):
                 ('param', c_double)]
 
 
+MAX_PEERS = 16
+EXCHANGE_BYTES = 2048
+
+
+class PeerExchange(Structure):
+    _fields_ = [('rank', c_int32), ('nranks', c_int32), ('tag', c_uint32), ('reserved', c_uint32),
+                ('n_total', c_int64), ('slots', c_void_p * MAX_PEERS)]
+
+
 class B200Error(RuntimeError):
     """A failing C-ABI call (status != 0)."""
 
@@ -111,6 +120,8 @@ _EXPORTS = {
     'b200_reduce_supported': (c_int, [POINTER(ReduceDesc)]),
     'b200_reduce_workspace_bytes': (c_int, [POINTER(ReduceDesc), POINTER(c_size_t)]),
     'b200_reduce_run': (c_int, [POINTER(ReduceDesc), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'b200_reduce_run_sharded': (c_int, [POINTER(ReduceDesc), c_void_p, c_void_p, c_void_p, c_size_t, POINTER(PeerExchange),
+                                        c_void_p]),
     'b200_moments_merge': (c_int, [c_void_p, c_int, c_double, c_void_p, c_void_p]),
     'b200_scan_supported': (c_int, [c_int, c_int, c_int]),
     'b200_scan_workspace_bytes': (c_int, [c_int64, c_int, POINTER(c_size_t)]),

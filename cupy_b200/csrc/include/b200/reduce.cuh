@@ -134,10 +134,82 @@ struct ThreadAcc {
 // partials in a fixed order -- one launch, one read of x, deterministic result.
 // workspace: gridDim.x partials + a zeroed uint32 ticket (left zeroed).
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// Cross-GPU combine fused into the last block of a FULL reduction (sharded sum / mean / var of
+// BASELINE config 5).  Every rank owns a small exchange buffer that all ranks of the node have mapped
+// (symmetric memory over NVLink / NVSwitch peer access).  The last block of rank r
+//   1. stores its partial accumulator, as 64-bit words {tag, 32 payload bits}, into slot [parity][r] of
+//      EVERY rank's buffer (plain st.global on the mapped peer pointers -- NVLink stores),
+//   2. spins on its OWN buffer until the words of all ranks carry this call's tag,
+//   3. folds the partials in rank order (bit-identical result on every rank) and applies post().
+// A word is written by one atomic 8-byte store, so a matching tag implies the payload: no fences, no
+// second launch, no NCCL small-message latency (replaces the ncclAllReduce(count=1) of
+// cupyx/distributed/_nccl_comm.py:312-320 -> cupy_backends/cuda/libs/nccl.pyx:470-477 for this path).
+// Slots are double-buffered by tag parity: a rank can only start call e+2 after every rank finished
+// call e (it needed their words of call e+1), so call e's words are never overwritten while in use.
+// ---------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;        // == B200_MAX_PEERS
+constexpr int kExWords = 8;          // accumulators up to 32 bytes
+struct PeerEx {
+    int32_t   rank, nranks;          // nranks <= 1: no exchange
+    uint32_t  tag, pad_;             // same on every rank, different from the previous call's, never 0
+    long long n_total;               // elements over all ranks (post() divides by it for mean / var)
+    uint64_t* slots[kMaxPeers];      // slots[r] = rank r's buffer: [2][kMaxPeers][kExWords] words, zeroed once
+};
+
+template <class Op, int THREADS>
+__device__ __forceinline__ typename Op::acc_t peer_allreduce(const Op& op, const typename Op::acc_t& mine,
+                                                             const PeerEx& ex) {
+    typedef typename Op::acc_t acc_t;
+    constexpr int W = (int(sizeof(acc_t)) + 3) / 4;
+    static_assert(W <= kExWords, "accumulator too large for the peer exchange");
+    static_assert(THREADS >= kMaxPeers * kExWords, "one thread per (rank, word)");
+    __shared__ uint32_t ex_mine[kExWords];
+    __shared__ uint32_t ex_words[kMaxPeers][kExWords];
+    if (threadIdx.x == 0) {
+        union U { acc_t a; uint32_t w[W]; B200_DEVICE U() {} } u;
+#pragma unroll
+        for (int w = 0; w < W; ++w) u.w[w] = 0u;
+        u.a = mine;
+#pragma unroll
+        for (int w = 0; w < W; ++w) ex_mine[w] = u.w[w];
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < ex.nranks * W) {
+        const int p = t / W, w = t % W;
+        const size_t base = size_t(ex.tag & 1u) * kMaxPeers * kExWords;
+        const uint64_t word = (uint64_t(ex.tag) << 32) | ex_mine[w];
+        uint64_t* dst = ex.slots[p] + base + size_t(ex.rank) * kExWords + w;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+        const uint64_t* src = ex.slots[ex.rank] + base + size_t(p) * kExWords + w;
+        uint64_t v;
+        uint32_t polls = 0;
+        do {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+            // a rank that never shows up (crashed peer, mismatched call order) must not hang the GPU: give up
+            // after ~2^26 polls (tens of seconds) with a trap, which the host sees as a launch failure
+            if (++polls == (1u << 26)) __trap();
+        } while (static_cast<uint32_t>(v >> 32) != ex.tag);
+        ex_words[p][w] = static_cast<uint32_t>(v);
+    }
+    __syncthreads();
+    union U { acc_t a; uint32_t w[W]; B200_DEVICE U() {} } u;
+#pragma unroll
+    for (int w = 0; w < W; ++w) u.w[w] = ex_words[0][w];
+    acc_t r = u.a;
+    for (int p = 1; p < ex.nranks; ++p) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) u.w[w] = ex_words[p][w];
+        r = op.combine(r, u.a);
+    }
+    return r;
+}
+
 template <class Op, int VEC, int UNROLL, int THREADS>
 __device__ __forceinline__ void reduce_full_body(
         const Op& op, typename in_ptr<Op>::type x, typename Op::out_t* __restrict__ y,
-        int64_t n, typename Op::acc_t* partials, uint32_t* ticket) {
+        int64_t n, typename Op::acc_t* partials, uint32_t* ticket, const PeerEx* ex = nullptr) {
     typedef typename Op::acc_t acc_t;
     typedef typename Op::index_t index_t;
     constexpr int64_t kTile = int64_t(THREADS) * VEC * UNROLL;
@@ -163,6 +235,10 @@ __device__ __forceinline__ void reduce_full_body(
     r = block_combine(op, r, smem);
 
     if (gridDim.x == 1) {
+        if (ex != nullptr && ex->nranks > 1) {
+            r = peer_allreduce<Op, THREADS>(op, r, *ex);
+            n = ex->n_total;
+        }
         if (threadIdx.x == 0) y[0] = op.post(r, n);
         return;
     }
@@ -181,6 +257,10 @@ __device__ __forceinline__ void reduce_full_body(
     for (int i = threadIdx.x; i < int(gridDim.x); i += THREADS)
         r = op.combine(r, load_volatile(partials + i));
     r = block_combine(op, r, smem);
+    if (ex != nullptr && ex->nranks > 1) {         // sharded: fold in the other GPUs' partials (block-uniform branch)
+        r = peer_allreduce<Op, THREADS>(op, r, *ex);
+        n = ex->n_total;
+    }
     if (threadIdx.x == 0) y[0] = op.post(r, n);
 }
 

@@ -6,26 +6,27 @@
 namespace b200 {
 
 #define B200_DECL(NAME) \
-    int reduce_run_##NAME(const b200_reduce_desc_t*, const void*, void*, void*, size_t, cudaStream_t, bool, size_t*);
+    int reduce_run_##NAME(const b200_reduce_desc_t*, const void*, void*, void*, size_t, cudaStream_t, bool, size_t*, \
+                          const b200_peer_exchange_t*);
 B200_DECL(f32) B200_DECL(f16) B200_DECL(f64) B200_DECL(i32) B200_DECL(i64) B200_DECL(i8) B200_DECL(u8) B200_DECL(b1)
 #undef B200_DECL
 
 static int dispatch(const b200_reduce_desc_t* d, const void* x, void* y, void* ws, size_t wsb,
-                    cudaStream_t s, bool query, size_t* need) {
+                    cudaStream_t s, bool query, size_t* need, const b200_peer_exchange_t* pex = nullptr) {
     if (!d) return fail(B200_E_INVALID, "null descriptor");
     if (d->n_reduce <= 0 || d->n_out <= 0 || d->batch <= 0)
         return fail(B200_E_INVALID, "empty reduction: the host handles zero-size arrays");
     if (d->layout != B200_RED_COLS && d->batch != 1) return fail(B200_E_INVALID, "batch is only defined for the COLS layout");
     if (d->layout == B200_RED_FULL && d->n_out != 1) return fail(B200_E_INVALID, "FULL layout has exactly one output");
     switch (d->in_dtype) {
-        case B200_TYPE_FLOAT32: return reduce_run_f32(d, x, y, ws, wsb, s, query, need);
-        case B200_TYPE_FLOAT16: return reduce_run_f16(d, x, y, ws, wsb, s, query, need);
-        case B200_TYPE_FLOAT64: return reduce_run_f64(d, x, y, ws, wsb, s, query, need);
-        case B200_TYPE_INT32:   return reduce_run_i32(d, x, y, ws, wsb, s, query, need);
-        case B200_TYPE_INT64:   return reduce_run_i64(d, x, y, ws, wsb, s, query, need);
-        case B200_TYPE_INT8:    return reduce_run_i8(d, x, y, ws, wsb, s, query, need);
-        case B200_TYPE_UINT8:   return reduce_run_u8(d, x, y, ws, wsb, s, query, need);
-        case B200_TYPE_BOOL:    return reduce_run_b1(d, x, y, ws, wsb, s, query, need);
+        case B200_TYPE_FLOAT32: return reduce_run_f32(d, x, y, ws, wsb, s, query, need, pex);
+        case B200_TYPE_FLOAT16: return reduce_run_f16(d, x, y, ws, wsb, s, query, need, pex);
+        case B200_TYPE_FLOAT64: return reduce_run_f64(d, x, y, ws, wsb, s, query, need, pex);
+        case B200_TYPE_INT32:   return reduce_run_i32(d, x, y, ws, wsb, s, query, need, pex);
+        case B200_TYPE_INT64:   return reduce_run_i64(d, x, y, ws, wsb, s, query, need, pex);
+        case B200_TYPE_INT8:    return reduce_run_i8(d, x, y, ws, wsb, s, query, need, pex);
+        case B200_TYPE_UINT8:   return reduce_run_u8(d, x, y, ws, wsb, s, query, need, pex);
+        case B200_TYPE_BOOL:    return reduce_run_b1(d, x, y, ws, wsb, s, query, need, pex);
         default:
             return fail(B200_E_UNSUPPORTED, "no prebuilt reduction for input dtype %d", d->in_dtype);
     }
@@ -80,4 +81,12 @@ extern "C" __attribute__((visibility("default"))) int b200_reduce_run(const b200
     if (!x || !y) return fail(B200_E_INVALID, "null data pointer");
     size_t need = 0;
     return dispatch(d, x, y, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), false, &need);
+}
+
+extern "C" __attribute__((visibility("default"))) int b200_reduce_run_sharded(const b200_reduce_desc_t* d, const void* x, void* y,
+                               void* workspace, size_t workspace_bytes, const b200_peer_exchange_t* exchange,
+                               void* stream) {
+    if (!x || !y || !exchange) return fail(B200_E_INVALID, "null pointer");
+    size_t need = 0;
+    return dispatch(d, x, y, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), false, &need, exchange);
 }

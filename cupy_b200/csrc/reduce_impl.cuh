@@ -6,6 +6,7 @@
 // cupy/_core/_reduction.pyx:239-253, 481-508; op / dtype codes are the
 // reference's (cupy_cub.h:4-11, type_dispatcher.cuh:15-28).
 #include <algorithm>
+#include <cstring>
 
 #pragma once
 #include "common.h"
@@ -22,8 +23,8 @@ constexpr size_t kTicketBytes = 16384;
 template <class Op, int VEC, int UNROLL>
 __global__ void __launch_bounds__(kRedThreads) reduce_full_kernel(
         Op op, const typename Op::in_t* x, typename Op::out_t* y, int64_t n,
-        typename Op::acc_t* partials, uint32_t* ticket) {
-    reduce_full_body<Op, VEC, UNROLL, kRedThreads>(op, x, y, n, partials, ticket);
+        typename Op::acc_t* partials, uint32_t* ticket, const __grid_constant__ PeerEx ex) {
+    reduce_full_body<Op, VEC, UNROLL, kRedThreads>(op, x, y, n, partials, ticket, &ex);
 }
 
 template <class Op, int VEC, int UNROLL, int GROUP>
@@ -92,10 +93,16 @@ static void cols_geometry(int64_t batch, int64_t n, int64_t cols, int vec, int s
     g->ticket_count = nsplit > 1 ? size_t(batch) * tiles : 0;
 }
 
+// which functors may be folded across GPUs by value: everything except the arg-reductions, whose
+// accumulators carry shard-local indices
+template <class Op> struct peer_exchangeable { static constexpr bool value = true; };
+template <class T, class I, bool kMax> struct peer_exchangeable<ArgOp<T, I, kMax>> { static constexpr bool value = false; };
+
 // ---- typed launch -------------------------------------------------------------
 template <class Op, int FULLVEC>
 static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, void* yv,
-                     void* ws, size_t ws_bytes, cudaStream_t stream, bool query, size_t* need) {
+                     void* ws, size_t ws_bytes, cudaStream_t stream, bool query, size_t* need,
+                     const b200_peer_exchange_t* pex = nullptr) {
     typedef typename Op::in_t in_t;
     typedef typename Op::out_t out_t;
     typedef typename Op::acc_t acc_t;
@@ -111,6 +118,22 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
     constexpr int CV = (8 * 32 * FULLVEC * int(sizeof(acc_t)) > 32768) ? FULLVEC / 2 : FULLVEC;
     constexpr int CU = 4;
 
+    if (pex != nullptr && !query) {
+        if (d->layout != B200_RED_FULL) return fail(B200_E_UNSUPPORTED, "the cross-GPU combine is fused into FULL reductions only");
+        if (Op::kWideIndex || sizeof(acc_t) > 4 * kExWords || !peer_exchangeable<Op>::value)
+            return fail(B200_E_UNSUPPORTED, "this reduction cannot be combined across GPUs in-kernel");
+        if (pex->nranks < 1 || pex->nranks > kMaxPeers || pex->rank < 0 || pex->rank >= pex->nranks || pex->tag == 0)
+            return fail(B200_E_INVALID, "bad peer exchange descriptor");
+    }
+    PeerEx ex;
+    std::memset(&ex, 0, sizeof(ex));
+    if (pex != nullptr && !query && pex->nranks > 1) {
+        ex.rank = pex->rank; ex.nranks = pex->nranks; ex.tag = pex->tag; ex.n_total = pex->n_total;
+        for (int r = 0; r < pex->nranks; ++r) {
+            if (!pex->slots[r]) return fail(B200_E_INVALID, "peer exchange: null slot pointer for rank %d", r);
+            ex.slots[r] = static_cast<uint64_t*>(pex->slots[r]);
+        }
+    }
     if (d->layout == B200_RED_FULL) {
         // workspace = [tickets: kTicketBytes][partials]; sized for the widest grid
         const size_t partial_bytes = size_t(di.sm_count) * 8 * sizeof(acc_t);
@@ -122,9 +145,9 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
         uint32_t* ticket = static_cast<uint32_t*>(ws);
         acc_t* partials = reinterpret_cast<acc_t*>(static_cast<char*>(ws) + kTicketBytes);
         if (vec == FULLVEC)
-            reduce_full_kernel<Op, FULLVEC, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket);
+            reduce_full_kernel<Op, FULLVEC, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket, ex);
         else
-            reduce_full_kernel<Op, 1, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket);
+            reduce_full_kernel<Op, 1, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket, ex);
     } else if constexpr (Op::kWideIndex) {
         // (value, 64-bit index) pairs are only built for FULL; the host routes
         // rows/cols with >= 2^31 reduced elements elsewhere
@@ -229,7 +252,7 @@ template <> struct out_id<bool> { static constexpr int v = B200_TYPE_BOOL; };
 
 template <class T>
 static int run_for_type(const b200_reduce_desc_t* d, const void* x, void* y, void* ws, size_t wsb,
-                        cudaStream_t s, bool query, size_t* need) {
+                        cudaStream_t s, bool query, size_t* need, const b200_peer_exchange_t* pex) {
     constexpr int FV = (16 / int(sizeof(T))) > 8 ? 8 : (16 / int(sizeof(T)));
     // index type of arg-reductions: 32 bit whenever the reduced extent allows
     const bool j32 = d->n_reduce < (int64_t(1) << 31);
@@ -237,38 +260,38 @@ static int run_for_type(const b200_reduce_desc_t* d, const void* x, void* y, voi
         case B200_OP_SUM: {
             typedef typename sum_acc<T>::type A; typedef typename sum_out<T>::type O;
             B200_REQUIRE_OUT(O);
-            return run_typed<SumOp<T, A, O>, FV>(SumOp<T, A, O>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<SumOp<T, A, O>, FV>(SumOp<T, A, O>(), d, x, y, ws, wsb, s, query, need, pex);
         }
         case B200_OP_PROD: {
             typedef typename sum_acc<T>::type A; typedef typename sum_out<T>::type O;
             B200_REQUIRE_OUT(O);
-            return run_typed<ProdOp<T, A, O>, FV>(ProdOp<T, A, O>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<ProdOp<T, A, O>, FV>(ProdOp<T, A, O>(), d, x, y, ws, wsb, s, query, need, pex);
         }
         case B200_OP_MIN:
             B200_REQUIRE_OUT(T);
-            return run_typed<MinMaxOp<T, false>, FV>(MinMaxOp<T, false>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<MinMaxOp<T, false>, FV>(MinMaxOp<T, false>(), d, x, y, ws, wsb, s, query, need, pex);
         case B200_OP_MAX:
             B200_REQUIRE_OUT(T);
-            return run_typed<MinMaxOp<T, true>, FV>(MinMaxOp<T, true>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<MinMaxOp<T, true>, FV>(MinMaxOp<T, true>(), d, x, y, ws, wsb, s, query, need, pex);
         case B200_OP_ARGMIN:
             B200_REQUIRE_OUT(long long);
-            if (j32) return run_typed<ArgOp<T, int, false>, FV>(ArgOp<T, int, false>(), d, x, y, ws, wsb, s, query, need);
-            return run_typed<ArgOp<T, long long, false>, FV>(ArgOp<T, long long, false>(), d, x, y, ws, wsb, s, query, need);
+            if (j32) return run_typed<ArgOp<T, int, false>, FV>(ArgOp<T, int, false>(), d, x, y, ws, wsb, s, query, need, pex);
+            return run_typed<ArgOp<T, long long, false>, FV>(ArgOp<T, long long, false>(), d, x, y, ws, wsb, s, query, need, pex);
         case B200_OP_ARGMAX:
             B200_REQUIRE_OUT(long long);
-            if (j32) return run_typed<ArgOp<T, int, true>, FV>(ArgOp<T, int, true>(), d, x, y, ws, wsb, s, query, need);
-            return run_typed<ArgOp<T, long long, true>, FV>(ArgOp<T, long long, true>(), d, x, y, ws, wsb, s, query, need);
+            if (j32) return run_typed<ArgOp<T, int, true>, FV>(ArgOp<T, int, true>(), d, x, y, ws, wsb, s, query, need, pex);
+            return run_typed<ArgOp<T, long long, true>, FV>(ArgOp<T, long long, true>(), d, x, y, ws, wsb, s, query, need, pex);
         case B200_OP_MEAN: {
             typedef typename mom_float<T>::type F; typedef typename mom_out<T>::type O;
             B200_REQUIRE_OUT(O);
-            return run_typed<MeanOp<T, F, O>, FV>(MeanOp<T, F, O>(), d, x, y, ws, wsb, s, query, need);
+            return run_typed<MeanOp<T, F, O>, FV>(MeanOp<T, F, O>(), d, x, y, ws, wsb, s, query, need, pex);
         }
         case B200_OP_VAR: {
             typedef typename mom_float<T>::type F; typedef typename mom_out<T>::type O;
             B200_REQUIRE_OUT(O);
             MomentsOp<T, F, O, kMomVar> op;
             op.ddof = F(d->param);
-            return run_typed<MomentsOp<T, F, O, kMomVar>, FV>(op, d, x, y, ws, wsb, s, query, need);
+            return run_typed<MomentsOp<T, F, O, kMomVar>, FV>(op, d, x, y, ws, wsb, s, query, need, pex);
         }
         case B200_OP_MOMENTS: {
             // y holds one (n, mean, M2) triple of doubles
@@ -277,7 +300,7 @@ static int run_for_type(const b200_reduce_desc_t* d, const void* x, void* y, voi
             if (d->layout != B200_RED_FULL) return fail(B200_E_UNSUPPORTED, "B200_OP_MOMENTS is a full reduction");
             MomentsOp<T, F, F, kMomPair> op;
             op.ddof = F(0);
-            return run_typed<MomentsOp<T, F, F, kMomPair>, FV>(op, d, x, y, ws, wsb, s, query, need);
+            return run_typed<MomentsOp<T, F, F, kMomPair>, FV>(op, d, x, y, ws, wsb, s, query, need, pex);
         }
         default:
             return fail(B200_E_INVALID, "op code %d is not a reduction", d->op);

@@ -20,6 +20,8 @@ class NCCLBackend:
     def __init__(self, n_devices, rank, backend='nccl', host='127.0.0.1', port=13333):
         self._n_devices = n_devices
         self.rank = rank
+        self._exchange = None          # (symmetric buffer, handle, peer pointers) | False when unavailable
+        self._tag = 0
         if not dist.is_initialized():
             if 'MASTER_ADDR' in os.environ and 'MASTER_PORT' in os.environ:
                 dist.init_process_group(backend, rank=rank, world_size=n_devices)
@@ -42,40 +44,91 @@ class NCCLBackend:
         t = a.reshape(-1) if a.flags.c_contiguous else a.T.reshape(-1)
         return t.to_torch()
 
+    @staticmethod
+    def _on(stream):
+        """`stream=` of every collective (cupyx/distributed/_nccl_comm.py:139-306): the collective is enqueued on
+        that stream (torch's NCCL work is ordered against the CURRENT stream, so the stream is made current)."""
+        from cupy_b200._core._ndarray import _stream_ctx
+        return _stream_ctx(stream)
+
     # -- collectives ----------------------------------------------------------------------
     def all_reduce(self, in_array, out_array, op='sum', stream=None):
-        src, dst = self._tensor(in_array), self._tensor(out_array)
-        if dst.data_ptr() != src.data_ptr():
-            dst.copy_(src)
-        dist.all_reduce(dst, op=_OPS[op])
+        with self._on(stream):
+            src, dst = self._tensor(in_array), self._tensor(out_array)
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src)
+            dist.all_reduce(dst, op=_OPS[op])
 
     def reduce(self, in_array, out_array, root=0, op='sum', stream=None):
-        src, dst = self._tensor(in_array), self._tensor(out_array)
-        if dst.data_ptr() != src.data_ptr():
-            dst.copy_(src)
-        dist.reduce(dst, dst=root, op=_OPS[op])
+        with self._on(stream):
+            src, dst = self._tensor(in_array), self._tensor(out_array)
+            if self.rank == root:
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src)
+                dist.reduce(dst, dst=root, op=_OPS[op])
+            else:
+                # NCCL leaves a non-root receive buffer untouched: reduce through a temporary instead of
+                # overwriting out_array with this rank's input
+                tmp = src.clone() if dst.data_ptr() != src.data_ptr() else dst
+                dist.reduce(tmp, dst=root, op=_OPS[op])
 
     def broadcast(self, in_out_array, root=0, stream=None):
-        dist.broadcast(self._tensor(in_out_array), src=root)
+        with self._on(stream):
+            dist.broadcast(self._tensor(in_out_array), src=root)
 
     def all_gather(self, in_array, out_array, count=None, stream=None):
-        dist.all_gather_into_tensor(self._tensor(out_array), self._tensor(in_array))
+        with self._on(stream):
+            dist.all_gather_into_tensor(self._tensor(out_array), self._tensor(in_array))
 
     def reduce_scatter(self, in_array, out_array, count=None, op='sum', stream=None):
-        dist.reduce_scatter_tensor(self._tensor(out_array), self._tensor(in_array), op=_OPS[op])
+        with self._on(stream):
+            dist.reduce_scatter_tensor(self._tensor(out_array), self._tensor(in_array), op=_OPS[op])
 
     def send(self, array, peer, stream=None):
-        dist.send(self._tensor(array), dst=peer)
+        with self._on(stream):
+            dist.send(self._tensor(array), dst=peer)
 
     def recv(self, out_array, peer, stream=None):
-        dist.recv(self._tensor(out_array), src=peer)
+        with self._on(stream):
+            dist.recv(self._tensor(out_array), src=peer)
 
     def send_recv(self, in_array, out_array, peer, stream=None):
         """Grouped send + receive with one peer (cupyx/distributed/_nccl_comm.py:385-395)."""
-        ops = [dist.P2POp(dist.isend, self._tensor(in_array), peer),
-               dist.P2POp(dist.irecv, self._tensor(out_array), peer)]
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+        with self._on(stream):
+            ops = [dist.P2POp(dist.isend, self._tensor(in_array), peer),
+                   dist.P2POp(dist.irecv, self._tensor(out_array), peer)]
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    # -- the fused exchange of sharded FULL reductions (b200_reduce_run_sharded) -------------------------
+    def peer_exchange(self):
+        """The per-rank exchange buffers every rank has mapped (torch symmetric memory: CUDA VMM handles
+        exchanged once, peers reachable over NVLink / NVSwitch), or None when they cannot be had (CPU / gloo
+        groups, no peer access, more than B200_MAX_PEERS ranks): callers then take the NCCL route."""
+        if self._exchange is None:
+            self._exchange = False
+            from cupy_b200 import _lib
+            if (self.backend == 'nccl' and torch.cuda.is_available() and 1 < self._n_devices <= _lib.MAX_PEERS
+                    and os.environ.get('B200_SHARDED_COMBINE', 'fused') != 'nccl'):
+                try:
+                    import torch.distributed._symmetric_memory as symm
+                    buf = symm.empty(_lib.EXCHANGE_BYTES // 8, dtype=torch.int64, device='cuda')
+                    buf.zero_()
+                    handle = symm.rendezvous(buf, dist.group.WORLD)
+                    ptrs = [int(q) for q in handle.buffer_ptrs]
+                    torch.cuda.synchronize()
+                    dist.barrier()                 # every rank's buffer is zeroed before anyone writes into it
+                    self._exchange = (buf, handle, ptrs)
+                except Exception as e:             # symmetric memory not available on this box: NCCL route
+                    import warnings
+                    warnings.warn('cupy_b200.distributed: fused cross-GPU combine unavailable (%s: %s); using NCCL'
+                                  % (type(e).__name__, e))
+                    self._exchange = False
+        return self._exchange or None
+
+    def next_tag(self):
+        self._tag = (self._tag % 0xffffffff) + 1       # 1 .. 2^32-1, never 0; alternates parity
+        return self._tag
 
     def _check_first_dim(self, name, which, array):
         if array.shape[0] != self._n_devices:
@@ -132,11 +185,56 @@ def init_process_group(n_devices, rank, *, backend='nccl', host=None, port=None,
 
 
 # ---- the sharded reductions of BASELINE.json config 5 ---------------------------------------
+def _sharded_full(x_local, comm, op, out, param=0.0, total_size=None):
+    """ONE launch per rank: single-pass partial over the shard with the cross-GPU combine fused into the kernel's
+    last block (b200_reduce_run_sharded).  Returns None when the fused route does not apply."""
+    import ctypes
+    from cupy_b200 import _lib
+    from cupy_b200._core import _reduction, _scalar, _workspace
+    from cupy_b200._core._kernel import current_stream_ptr
+    ex = comm.peer_exchange() if hasattr(comm, 'peer_exchange') else None
+    if ex is None or x_local.size == 0:
+        return None
+    layout = _reduction._classify(x_local.shape, x_local.strides, x_local.dtype.itemsize,
+                                  tuple(range(x_local.ndim)), (), False)
+    if layout.kind != _lib.RED_FULL:
+        return None
+    desc = _lib.ReduceDesc(op, _lib.RED_FULL, _scalar.dtype_id(x_local.dtype), _scalar.dtype_id(out.dtype),
+                           1, layout.n_reduce, 1, float(param))
+    if not _lib.lib.b200_reduce_supported(ctypes.byref(desc)):
+        return None
+    world = comm._n_devices
+    pe = _lib.PeerExchange()
+    pe.rank, pe.nranks, pe.tag = comm.rank, world, comm.next_tag()
+    pe.n_total = int(total_size) if total_size is not None else x_local.size * world
+    for r, q in enumerate(ex[2]):
+        pe.slots[r] = q
+    st = current_stream_ptr()
+    need = ctypes.c_size_t()
+    _lib.check(_lib.lib.b200_reduce_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
+    ws_ptr, ws_bytes = _workspace.get(need.value, st)
+    _lib.check(_lib.lib.b200_reduce_run_sharded(ctypes.byref(desc), x_local.ptr, out.ptr, ws_ptr, ws_bytes,
+                                                ctypes.byref(pe), st))
+    return out
+
+
+def _sum_dtype(dt):
+    return numpy.dtype('int64') if dt.kind in 'bi' else numpy.dtype('uint64') if dt.kind == 'u' else dt
+
+
 def sharded_sum(x_local, comm, out=None):
-    """Sum of a 1-D array sharded over the ranks: per-GPU single-pass partial
-    (b200 reduce_full) followed by ONE all-reduce of the 0-d partial
-    (cupyx/distributed/_nccl_comm.py:139-152 recipe).  Every rank gets the result."""
-    part = x_local.sum() if out is None else x_local.sum(out=out)
+    """Sum of an array sharded over the ranks; every rank gets the result (bit-identical).
+
+    Default route: one kernel per GPU -- the single-pass full reduction whose last block exchanges the
+    per-GPU partials through NVLink peer memory and folds them in rank order (b200_reduce_run_sharded).
+    Fallback (no symmetric memory / gloo / B200_SHARDED_COMBINE=nccl): per-GPU partial followed by ONE
+    all-reduce of the 0-d partial, the recipe of cupyx/distributed/_nccl_comm.py:139-152."""
+    from cupy_b200 import _lib
+    from cupy_b200._core._ndarray import ndarray
+    res = out if out is not None else ndarray((), _sum_dtype(x_local.dtype))
+    if _sharded_full(x_local, comm, _lib.OP_SUM, res) is not None:
+        return res
+    part = x_local.sum(out=res)
     comm.all_reduce(part, part, 'sum')
     return part
 
@@ -158,23 +256,32 @@ def combine_moments(counts, means, m2s):
     return n, mean, m2
 
 
-def sharded_var(x_local, comm, ddof=0):
-    """Variance of a 1-D array sharded over the ranks (the reference has no
-    distributed var, cupyx/distributed/array/_array.py:744-747; the oracle is
-    numpy.var of the gathered array).  ONE pass over the shard gives (mean, M2)
-    (B200_OP_MOMENTS), then one all-gather of 3 doubles per rank and a Chan merge in
-    rank order, so every rank computes the bit-identical result."""
-    import numpy
+def sharded_var(x_local, comm, ddof=0, total_size=None):
+    """Variance of an array sharded over the ranks (the reference has no distributed var,
+    cupyx/distributed/array/_array.py:744-747; the oracle is numpy.var of the gathered array).  Returns a
+    0-d cupy_b200.ndarray, bit-identical on every rank.
+
+    Default route: ONE launch per GPU -- the single-pass (n, mean, M2) reduction of the shard with the Chan
+    merge over the ranks (rank order) fused into its last block through NVLink peer memory.  `total_size`
+    is the global element count (default: equal shards).  Fallback: B200_OP_MOMENTS + one all-gather of 3
+    doubles through `comm` + b200_moments_merge."""
     from cupy_b200 import _lib
     from cupy_b200._core._ndarray import ndarray
     from cupy_b200._core._kernel import current_stream_ptr
     from cupy_b200._core._routines_statistics import moments
-    world = dist.get_world_size() if dist.is_initialized() else 1
+    out_dt = numpy.dtype('float64') if x_local.dtype.kind in 'biu' else x_local.dtype
+    res = ndarray((), out_dt)
+    if _sharded_full(x_local, comm, _lib.OP_VAR, res, param=float(ddof), total_size=total_size) is not None:
+        return res
+    world = comm._n_devices if hasattr(comm, '_n_devices') else 1
+    rank = comm.rank if hasattr(comm, 'rank') else 0
     buf = ndarray((world + 1, 3), numpy.float64)         # rows 0..world-1: gathered triples; last row: result
-    bt = buf.to_torch()
-    rank = dist.get_rank() if world > 1 else 0
-    moments(x_local, out=buf[rank])
+    mine = ndarray((3,), numpy.float64)
+    moments(x_local, out=mine)
     if world > 1:
-        dist.all_gather_into_tensor(bt[:world].reshape(-1), bt[rank])
+        comm.all_gather(mine, buf[:world], 3)
+    else:
+        from cupy_b200._core._kernel import elementwise_copy
+        elementwise_copy(mine, buf[0])
     _lib.check(_lib.lib.b200_moments_merge(buf.ptr, world, float(ddof), buf[world].ptr, current_stream_ptr()))
-    return bt[world, 0]
+    return buf[world, 0].astype(out_dt) if out_dt != numpy.float64 else buf[world, 0]

@@ -206,6 +206,26 @@ int b200_reduce_workspace_bytes(const b200_reduce_desc_t* d, size_t* bytes);
 int b200_reduce_run(const b200_reduce_desc_t* d, const void* x, void* y,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Sharded FULL reduction with the cross-GPU combine fused into the kernel's last block: every rank
+ * runs this call on its shard; the per-GPU partial accumulators are exchanged through `slots` -- one small
+ * buffer per rank that every rank has mapped (symmetric memory over NVLink / NVSwitch peer access), written
+ * with plain stores on the mapped peer pointers -- folded in rank order and post-processed with the TOTAL
+ * element count, so that y holds the global sum / prod / min / max / mean / var, bit-identical on every rank,
+ * after ONE launch.  Replaces per-GPU reduction + ncclAllReduce(count=1) (cupyx/distributed/_nccl_comm.py:
+ * 312-320 -> cupy_backends/cuda/libs/nccl.pyx:470-477).  Collective: every rank must make the same call in the
+ * same order on one stream.  B200_E_UNSUPPORTED for arg-reductions and non-FULL layouts. */
+#define B200_MAX_PEERS 16
+#define B200_EXCHANGE_BYTES 2048     /* per-rank buffer: [2 parities][16 sources][8 words] x 8 bytes; zeroed once */
+typedef struct b200_peer_exchange {
+    int32_t  rank, nranks;
+    uint32_t tag;                    /* per-communicator call counter: same on every rank, changes every call, != 0 */
+    uint32_t reserved;
+    int64_t  n_total;                /* elements over all ranks */
+    void*    slots[B200_MAX_PEERS];  /* slots[r] = rank r's exchange buffer as mapped into this process */
+} b200_peer_exchange_t;
+int b200_reduce_run_sharded(const b200_reduce_desc_t* d, const void* x, void* y, void* workspace, size_t workspace_bytes,
+                            const b200_peer_exchange_t* exchange, void* stream);
+
 /* Sharded variance (the reference has no distributed var, cupyx/distributed/array/_array.py:744-747):
  * Chan merge, in index order, of `count` (n, mean, M2) double triples as written by B200_OP_MOMENTS and
  * all-gathered over the ranks.  out[0] = M2 / (n - ddof) (NaN when n - ddof <= 0), out[1] = mean, out[2] = n. */

@@ -117,6 +117,11 @@ int main(int argc, char** argv) {
         CK(cudaEventRecord(e0)); CK(cudaMemcpyAsync(y, x, n * 8, cudaMemcpyDeviceToDevice)); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         CK(cudaEventElapsedTime(&ms, e0, e1));
         printf("%-58s n=%lld  %8.3f ms  %8.1f GB/s\n", "cudaMemcpy D2D", (long long)n, ms, 16.0 * n / ms / 1e6);
+        if (argc > 2) {      // profiling mode: one configuration only
+            bench<ScanPipeCfg<T, T, T, 8, 4, 2, 2>>("i64 pipe IPT8 SI4 SO2 LAG2", n, x, y, yref, ws, sm, 16);
+            bench<ScanPipeCfg<T, T, T, 4, 6, 3, 2>>("i64 pipe IPT4 SI6 SO3 LAG2 (16 KB stages)", n, x, y, yref, ws, sm, 16);
+            return 0;
+        }
         bench<ScanPipeCfg<T, T, T, 8, 4, 2, 1>, 2>("i64 pipe copy-only  IPT8 SI4 SO2", n, x, y, yref, ws, sm, 16);
         bench<ScanPipeCfg<T, T, T, 8, 4, 2, 1>, 1>("i64 pipe no-exchange IPT8 SI4 SO2 LAG1", n, x, y, yref, ws, sm, 16);
         bench<ScanPipeCfg<T, T, T, 8, 4, 2, 1>>("i64 pipe IPT8 SI4 SO2 LAG1", n, x, y, yref, ws, sm, 16);
