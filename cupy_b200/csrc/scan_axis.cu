@@ -24,7 +24,7 @@ namespace b200 {
 
 // ------------------------------------------------------------------------------------------
 // carry_in (optional): exclusive prefix each line starts from; total (>= 0): the lines are consecutive
-// chunks of a FLAT array of `total` elements, the last one ragged (flat casting scans, see scan_flat_lines).
+// chunks of a FLAT array of `total` elements, the last one ragged.
 // W256 (compile time): 32-byte packs (8-byte items) move with one 256-bit access; the host guarantees
 // 32-byte aligned lines for them.
 template <class In, class Acc, class Out, class Op, int GROUP, int ITEMS, bool W256 = false>
@@ -233,105 +233,6 @@ static int run_axis(const void* xv, void* yv, int64_t outer, int64_t n, int64_t 
     B200_CUDA_TRY(cudaPeekAtLastError());
     return 0;
 }
-
-// ------------------------------------------------------------------------------------------
-// Flat scans whose dtypes the TMA scan does not take (casting scans: int32 -> int64, bool -> int64,
-// float16 with a float accumulator ...).  The classic one-tile-per-block look-back (scan.cuh) walks
-// back over every tile in flight (~900 on 148 SMs) and runs at 20-28 % of peak.  Instead the array is
-// cut into L consecutive lines: (1) line totals, (2) exclusive scan of the L totals by one block,
-// (3) the line scan above, each line starting from its carry.  x is read twice: 16 instead of 12 bytes
-// per int32 -> int64 element, at ~90 % of the DRAM rate.
-template <class In, class Acc, class Op>
-__global__ void __launch_bounds__(256) line_totals_kernel(const In* __restrict__ x, Acc* __restrict__ tot, int64_t lines,
-                                                          int64_t n_line, int64_t total, int vec_ok) {
-    constexpr int V = (16 / int(sizeof(In))) < 1 ? 1 : 16 / int(sizeof(In));
-    __shared__ Acc warp_tot[8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t line = blockIdx.x; line < lines; line += gridDim.x) {
-        const In* xl = x + line * n_line;
-        const int64_t left = total - line * n_line;
-        const int64_t n = left < n_line ? left : n_line;
-        Acc acc = Op::template identity<Acc>();
-        int64_t i = 0;
-        if (vec_ok) {
-            for (i = int64_t(threadIdx.x) * V; i + V <= n; i += int64_t(256) * V) {
-                Pack<In, V> v;
-                load_pack(v, xl + i);
-#pragma unroll
-                for (int k = 0; k < V; ++k) acc = Op::combine(acc, static_cast<Acc>(v[k]));
-            }
-            i = (n / V) * V + threadIdx.x;
-        } else {
-            i = threadIdx.x;
-        }
-        for (; i < n; i += 256) acc = Op::combine(acc, static_cast<Acc>(xl[i]));
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) acc = Op::combine(acc, shfl_down_any(acc, d));
-        if (lane == 0) warp_tot[warp] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            Acc t = warp_tot[0];
-#pragma unroll
-            for (int w = 1; w < 8; ++w) t = Op::combine(t, warp_tot[w]);
-            tot[line] = t;
-        }
-        __syncthreads();
-    }
-}
-
-// exclusive scan of the (few thousand) line totals, in place, by one block; sequential per thread chunk
-template <class Acc, class Op>
-__global__ void __launch_bounds__(256) carry_scan_kernel(Acc* __restrict__ tot, int64_t lines) {
-    __shared__ Acc part[256];
-    const int t = threadIdx.x;
-    const int64_t per = (lines + 255) / 256, lo = t * per, hi = (lo + per < lines) ? lo + per : lines;
-    Acc acc = Op::template identity<Acc>();
-    for (int64_t i = lo; i < hi; ++i) acc = Op::combine(acc, tot[i]);
-    part[t] = acc;
-    __syncthreads();
-    Acc before = Op::template identity<Acc>();
-    for (int k = 0; k < t; ++k) before = Op::combine(before, part[k]);
-    for (int64_t i = lo; i < hi; ++i) {
-        const Acc v = tot[i];
-        tot[i] = before;
-        before = Op::combine(before, v);
-    }
-}
-
-template <class In, class Acc, class Out, class Op>
-int scan_flat_lines(const In* x, Out* y, int64_t n, void* ws, size_t ws_bytes, int sm_count, cudaStream_t s) {
-    constexpr int ITEMS = (16 / int(sizeof(In))) < 4 ? 4 : (16 / int(sizeof(In)));
-    constexpr int64_t kTile = 256 * ITEMS;
-    // lines: a multiple of the tile (so every line starts aligned when x and y are), ~8 per SM
-    int64_t lines = std::min<int64_t>(int64_t(sm_count) * 8, (n + kTile * 8 - 1) / (kTile * 8));
-    lines = std::max<int64_t>(lines, 1);
-    const int64_t n_line = ((n + lines - 1) / lines + kTile - 1) / kTile * kTile;
-    lines = (n + n_line - 1) / n_line;
-    if (ws_bytes < size_t(lines) * sizeof(Acc) || !ws) return B200_E_WORKSPACE;
-    Acc* tot = static_cast<Acc*>(ws);
-    const uintptr_t xa = reinterpret_cast<uintptr_t>(x), ya = reinterpret_cast<uintptr_t>(y);
-    constexpr int in_al = int(sizeof(In)) * ITEMS >= 16 ? 16 : int(sizeof(In)) * ITEMS;
-    constexpr int out_al = int(sizeof(Out)) * ITEMS >= 16 ? 16 : int(sizeof(Out)) * ITEMS;
-    const int in_vec = xa % 16 == 0, out_vec = ya % out_al == 0;
-    line_totals_kernel<In, Acc, Op><<<unsigned(lines), 256, 0, s>>>(x, tot, lines, n_line, n, in_vec);
-    carry_scan_kernel<Acc, Op><<<1, 256, 0, s>>>(tot, lines);
-    constexpr bool k256 = sizeof(In) * ITEMS == 32 || sizeof(Out) * ITEMS == 32;
-    const bool iv = in_vec && (xa % in_al == 0);
-    const bool w256 = k256 && iv && out_vec && (sizeof(In) * ITEMS != 32 || xa % 32 == 0) &&
-                      (sizeof(Out) * ITEMS != 32 || ya % 32 == 0);          // n_line is a multiple of the tile
-    if (w256)
-        scan_lines_kernel<In, Acc, Out, Op, 256, ITEMS, k256><<<unsigned(lines), 256, 0, s>>>(x, y, lines, n_line, 1, 1, tot, n);
-    else
-        scan_lines_kernel<In, Acc, Out, Op, 256, ITEMS><<<unsigned(lines), 256, 0, s>>>(x, y, lines, n_line, iv, out_vec, tot, n);
-    return 0;
-}
-
-// explicit instantiations for the dtype table (called from scan.cu)
-#define X(I, O, TI, TA, TO)                                                                                         \
-    template int scan_flat_lines<TI, TA, TO, ScanSum>(const TI*, TO*, int64_t, void*, size_t, int, cudaStream_t);   \
-    template int scan_flat_lines<TI, TA, TO, ScanProd>(const TI*, TO*, int64_t, void*, size_t, int, cudaStream_t);
-B200_SCAN_TABLE(X)
-#undef X
 
 }  // namespace b200
 
