@@ -23,6 +23,15 @@ constexpr size_t kTicketBytes = 16384;
 template <class Op, int VEC, int UNROLL>
 __global__ void __launch_bounds__(kRedThreads) reduce_full_kernel(
         Op op, const typename Op::in_t* x, typename Op::out_t* y, int64_t n,
+        typename Op::acc_t* partials, uint32_t* ticket) {
+    reduce_full_body<Op, VEC, UNROLL, kRedThreads>(op, x, y, n, partials, ticket);
+}
+
+// the sharded variant (cross-GPU combine in the last block) is a separate instantiation: its extra
+// registers and shared memory would cost the plain kernel a resident block per SM (sum 2^28: -7 %)
+template <class Op, int VEC, int UNROLL>
+__global__ void __launch_bounds__(kRedThreads) reduce_full_sharded_kernel(
+        Op op, const typename Op::in_t* x, typename Op::out_t* y, int64_t n,
         typename Op::acc_t* partials, uint32_t* ticket, const __grid_constant__ PeerEx ex) {
     reduce_full_body<Op, VEC, UNROLL, kRedThreads>(op, x, y, n, partials, ticket, &ex);
 }
@@ -144,10 +153,20 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
             return fail(B200_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, kTicketBytes + partial_bytes);
         uint32_t* ticket = static_cast<uint32_t*>(ws);
         acc_t* partials = reinterpret_cast<acc_t*>(static_cast<char*>(ws) + kTicketBytes);
+        if constexpr (peer_exchangeable<Op>::value && !Op::kWideIndex && sizeof(acc_t) <= 4 * kExWords) {
+            if (ex.nranks > 1) {
+                if (vec == FULLVEC)
+                    reduce_full_sharded_kernel<Op, FULLVEC, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket, ex);
+                else
+                    reduce_full_sharded_kernel<Op, 1, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket, ex);
+                B200_CUDA_TRY(cudaPeekAtLastError());
+                return 0;
+            }
+        }
         if (vec == FULLVEC)
-            reduce_full_kernel<Op, FULLVEC, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket, ex);
+            reduce_full_kernel<Op, FULLVEC, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket);
         else
-            reduce_full_kernel<Op, 1, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket, ex);
+            reduce_full_kernel<Op, 1, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket);
     } else if constexpr (Op::kWideIndex) {
         // (value, 64-bit index) pairs are only built for FULL; the host routes
         // rows/cols with >= 2^31 reduced elements elsewhere
