@@ -157,9 +157,11 @@ struct PeerEx {
     uint64_t* slots[kMaxPeers];      // slots[r] = rank r's buffer: [2][kMaxPeers][kExWords] words, zeroed once
 };
 
+// __noinline__: run once, by the last block; keeping it out of line leaves the register allocation and load
+// batching of the streaming loop exactly as in the plain kernel
 template <class Op, int THREADS>
-__device__ __forceinline__ typename Op::acc_t peer_allreduce(const Op& op, const typename Op::acc_t& mine,
-                                                             const PeerEx& ex) {
+__device__ __noinline__ typename Op::acc_t peer_allreduce(const Op& op, const typename Op::acc_t& mine,
+                                                          const PeerEx& ex) {
     typedef typename Op::acc_t acc_t;
     constexpr int W = (int(sizeof(acc_t)) + 3) / 4;
     static_assert(W <= kExWords, "accumulator too large for the peer exchange");

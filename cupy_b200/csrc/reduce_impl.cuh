@@ -68,10 +68,26 @@ static int pick_vec(const void* x, int64_t inner, int itemsize) {
     return vec;
 }
 
-static int full_grid(int64_t n, int vec, int unroll, int sm) {
+// FULL reductions are persistent: exactly as many blocks as the device holds at once (occupancy of the very
+// instantiation x SMs), each striding over an equal share -- one wave, no tail (a fixed 8 blocks per SM left
+// a partially filled second wave for every functor whose registers allow only 5 or 6 resident blocks)
+static int full_grid(int64_t n, int vec, int unroll, int sm, int blocks_per_sm) {
     const int64_t tile = int64_t(kRedThreads) * vec * unroll;
     const int64_t tiles = (n + tile - 1) / tile;
-    return int(std::max<int64_t>(1, std::min<int64_t>(tiles, int64_t(sm) * 8)));
+    return int(std::max<int64_t>(1, std::min<int64_t>(tiles, int64_t(sm) * blocks_per_sm)));
+}
+
+template <class Op, int VEC, int UNROLL, bool SHARDED>
+static int full_blocks_per_sm() {
+    static int occ = 0;      // per instantiation; benign race
+    if (!occ) {
+        int o = 0;
+        cudaError_t e;
+        if constexpr (SHARDED) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, reduce_full_sharded_kernel<Op, VEC, UNROLL>, kRedThreads, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, reduce_full_kernel<Op, VEC, UNROLL>, kRedThreads, 0);
+        occ = (e == cudaSuccess && o > 0) ? std::min(o, 8) : 8;
+    }
+    return occ;
 }
 
 // threads per row: the largest group whose unrolled tile (group * vec * unroll) still fits the row,
@@ -148,14 +164,16 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
         const size_t partial_bytes = size_t(di.sm_count) * 8 * sizeof(acc_t);
         if (query) { *need = kTicketBytes + align_up(size_t(296) * 8 * sizeof(acc_t), 16); return 0; }
         const int vec = pick_vec<FULLVEC>(x, d->n_reduce, sizeof(in_t));
-        const int grid = full_grid(d->n_reduce, vec, U, di.sm_count);
-        if (grid > 1 && ws_bytes < kTicketBytes + partial_bytes)
-            return fail(B200_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, kTicketBytes + partial_bytes);
+        const bool fullvec = vec == FULLVEC;
         uint32_t* ticket = static_cast<uint32_t*>(ws);
         acc_t* partials = reinterpret_cast<acc_t*>(static_cast<char*>(ws) + kTicketBytes);
         if constexpr (peer_exchangeable<Op>::value && !Op::kWideIndex && sizeof(acc_t) <= 4 * kExWords) {
             if (ex.nranks > 1) {
-                if (vec == FULLVEC)
+                const int bps = fullvec ? full_blocks_per_sm<Op, FULLVEC, U, true>() : full_blocks_per_sm<Op, 1, U, true>();
+                const int grid = full_grid(d->n_reduce, fullvec ? FULLVEC : 1, U, di.sm_count, bps);
+                if (grid > 1 && ws_bytes < kTicketBytes + partial_bytes)
+                    return fail(B200_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, kTicketBytes + partial_bytes);
+                if (fullvec)
                     reduce_full_sharded_kernel<Op, FULLVEC, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket, ex);
                 else
                     reduce_full_sharded_kernel<Op, 1, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket, ex);
@@ -163,7 +181,11 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
                 return 0;
             }
         }
-        if (vec == FULLVEC)
+        const int bps = fullvec ? full_blocks_per_sm<Op, FULLVEC, U, false>() : full_blocks_per_sm<Op, 1, U, false>();
+        const int grid = full_grid(d->n_reduce, fullvec ? FULLVEC : 1, U, di.sm_count, bps);
+        if (grid > 1 && ws_bytes < kTicketBytes + partial_bytes)
+            return fail(B200_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, kTicketBytes + partial_bytes);
+        if (fullvec)
             reduce_full_kernel<Op, FULLVEC, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket);
         else
             reduce_full_kernel<Op, 1, U><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_reduce, partials, ticket);
