@@ -418,13 +418,14 @@ def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stre
         _dryrun.record('jit_elementwise', name=name, variant=variant, vec=vec, ndim=plan.ndim,
                        idx32=bool(plan.idx32), staged_mask=plan.staged_mask, tile_axis=plan.tile_axis,
                        shape=tuple(plan.shape[:plan.ndim]), source=spec.last_source)
-        return
+        return fn.handle, threads
     st = current_stream_ptr() if stream is None else _stream_ptr(stream)
     if ind_ndim:
         shp = (ctypes.c_int64 * ind_ndim)(*ind_shape)
         _lib.check(_lib.lib.b200_jit_ew_launch_ex(fn.handle, ctypes.byref(plan), len(args), ops, threads, ind_ndim, shp, st))
     else:
         _lib.check(_lib.lib.b200_jit_ew_launch_ex(fn.handle, ctypes.byref(plan), len(args), ops, threads, 0, None, st))
+    return fn.handle, threads
 
 
 def _stream_ptr(stream):
@@ -704,6 +705,59 @@ class _Ops:
         return None
 
 
+# ---------------------------------------------------------------------------
+# Call-shape memo of the ufunc launcher.  Everything `ufunc.__call__` derives from the call's SHAPE --
+# loop selection, broadcasting, output dtype / shape, the collapsed plan, prebuilt-vs-NVRTC routing -- depends
+# only on (dtype, shape, strides, pointer alignment) of the array arguments and the types of the scalar ones.
+# The first call of a shape goes through the full path and leaves the filled C structures behind; later calls
+# patch the data pointers / scalar bytes into them and launch: one dict lookup and one ctypes crossing instead
+# of ~30 us of Python (the reference spends 12-20 us in Cython here, docs/source/user_guide/performance.rst).
+# Entries hold mutable ctypes buffers, so the memo is per thread.
+# ---------------------------------------------------------------------------
+_MISS = object()
+_FAST_MAX = 512
+
+
+def _fast_key(args, out):
+    key = []
+    for a in args:
+        ta = type(a)
+        if ta is ndarray:
+            key.append((a.dtype, a._shape, a._strides, a.ptr & 15))
+        elif ta is float or ta is bool:
+            key.append(ta)
+        elif ta is int:
+            if not -(1 << 63) <= a < (1 << 63):
+                return None
+            key.append(ta)
+        elif isinstance(a, numpy.generic):
+            key.append(a.dtype)
+        else:
+            return None
+    if out is not None:
+        if type(out) is not ndarray:
+            return None
+        key.append((out.dtype, out._shape, out._strides, out.ptr & 15, 'out'))
+    return tuple(key)
+
+
+class _FastEntry:
+    __slots__ = ('ops', 'plan', 'nargs', 'prebuilt', 'handle', 'threads', 'array_slots', 'scalar_slots',
+                 'out_slot', 'out_dtype', 'out_shape', 'out_strides', 'out_size', 'empty', 'dry')
+
+
+def _scalar_words(value, dtype, weak_t, lo, hi):
+    """The two 64-bit words of a by-value scalar operand cast to `dtype` (CScalar.apply_dtype + raw_bytes)."""
+    if weak_t is int and lo is not None and not (lo <= value <= hi):
+        raise OverflowError('Python integer %d out of bounds for %s' % (value, dtype))
+    if dtype.kind == 'b':
+        value = bool(value)
+    with numpy.errstate(over='ignore', invalid='ignore'):
+        b = numpy.asarray(value).astype(dtype, casting='unsafe').tobytes()
+    b = b + b'\0' * (16 - len(b))
+    return int.from_bytes(b[:8], 'little', signed=True), int.from_bytes(b[8:16], 'little', signed=True)
+
+
 class ufunc:
     """Universal function (drop-in for cupy.ufunc, cupy/_core/_kernel.pyx:1147-1493)."""
 
@@ -739,10 +793,27 @@ class ufunc:
                 for op in self._ops.ops]
 
     def __call__(self, *args, **kwargs):
+        fusing = getattr(_thread_local, 'fusion', None)
+        # ---- memoised call shape (plain arrays / scalars, at most an `out=`)
+        fkey = None
+        if fusing is None and (not kwargs or (len(kwargs) == 1 and 'out' in kwargs)):
+            fout = kwargs.get('out') if kwargs else None
+            if len(args) == self.nin or (fout is None and len(args) == self.nargs and self.nout == 1):
+                if len(args) == self.nargs and self.nout == 1 and fout is None:
+                    fkey = _fast_key(args[:self.nin], args[self.nin])
+                    fout = args[self.nin]
+                else:
+                    fkey = _fast_key(args, fout)
+                if fkey is not None:
+                    memo = _thread_local.__dict__.setdefault('ufunc_memo', {}).setdefault(id(self), {})
+                    entry = memo.get(fkey)
+                    if entry is not None:
+                        r = self._fast_launch(entry, args, fout)
+                        if r is not _MISS:
+                            return r
         for arg in args:
             if hasattr(arg, '__cupy_override_elementwise_kernel__'):
                 return arg.__cupy_override_elementwise_kernel__(self, *args, **kwargs)
-        fusing = getattr(_thread_local, 'fusion', None)
         if fusing is not None:
             return fusing.call_ufunc(self, *args, **kwargs)
 
@@ -789,8 +860,11 @@ class ufunc:
         else:
             where_args = []
 
+        ids_before = [id(a) for a in in_args]
         _copy_in_args_if_needed(in_args, given_out_args)
         _copy_in_args_if_needed(where_args, given_out_args)
+        if fkey is not None and ids_before != [id(a) for a in in_args]:
+            fkey = None                      # an input was copied because it overlaps the output: not memoised
         inout_args = in_args + where_args + given_out_args
         shape = _broadcast_core(inout_args)
         in_args = inout_args[:self.nin]
@@ -801,6 +875,7 @@ class ufunc:
         ret = out_args[0] if self.nout == 1 else tuple(out_args)
         if 0 in shape:
             return ret
+        weak_ts = [a.weak_t if isinstance(a, CScalar) else None for a in in_args]
         for i, t in enumerate(op.in_types):
             if isinstance(in_args[i], CScalar):
                 in_args[i].apply_dtype(t)
@@ -827,14 +902,80 @@ class ufunc:
                     _dryrun.record('prebuilt_ufunc', name=self.name, variant=plan.variant, vec=plan.vec,
                                    ndim=plan.ndim, idx32=bool(plan.idx32), staged_mask=plan.staged_mask,
                                    tile_axis=plan.tile_axis, shape=tuple(plan.shape[:plan.ndim]))
-                    return ret
-                _lib.check(_lib.lib.b200_ufunc_launch(self._prebuilt, ctypes.byref(plan), len(all_args), ops, st))
+                else:
+                    _lib.check(_lib.lib.b200_ufunc_launch(self._prebuilt, ctypes.byref(plan), len(all_args), ops, st))
+                if fkey is not None and not has_where and self.nout == 1:
+                    self._remember(fkey, ops, plan, all_args, op, weak_ts, out_args[0], self._prebuilt, None, 0)
                 return ret
 
         # ---- NVRTC route: the routine string inside the same tiler glue
         spec = self._get_spec(op, has_where)
-        _launch_jit(self._kernel_name(all_args, has_where), spec, all_args, params, n_in, ops, plan)
+        handle, threads = _launch_jit(self._kernel_name(all_args, has_where), spec, all_args, params, n_in, ops, plan)
+        if fkey is not None and not has_where and self.nout == 1:
+            self._remember(fkey, ops, plan, all_args, op, weak_ts, out_args[0], None, handle, threads)
         return ret
+
+    def _remember(self, fkey, ops, plan, all_args, op, weak_ts, out, prebuilt, handle, threads):
+        memo = _thread_local.__dict__.setdefault('ufunc_memo', {}).setdefault(id(self), {})
+        if len(memo) >= _FAST_MAX:
+            memo.clear()
+        e = _FastEntry()
+        e.ops, e.plan, e.nargs = ops, plan, len(all_args)
+        e.prebuilt, e.handle, e.threads = prebuilt, handle, threads
+        e.array_slots, e.scalar_slots = [], []
+        for k in range(self.nin):
+            a = all_args[k]
+            if isinstance(a, ndarray):
+                e.array_slots.append(k)
+            else:
+                t = op.in_types[k]
+                lo = hi = None
+                if t.kind in 'iu':
+                    info = numpy.iinfo(t)
+                    lo, hi = int(info.min), int(info.max)
+                e.scalar_slots.append((k, t, weak_ts[k], lo, hi, {}))
+        e.out_slot = len(all_args) - 1
+        e.out_dtype, e.out_shape, e.out_strides, e.out_size = out.dtype, out._shape, out._strides, out.size
+        e.empty = out._c_contiguous
+        e.dry = dict(_dryrun.log[-1]) if (_dryrun.enabled and _dryrun.log) else None
+        memo[fkey] = e
+
+    def _fast_launch(self, e, args, out):
+        """A call whose shape has been seen: patch pointers and scalar bytes into the remembered operand block."""
+        if out is not None:
+            for k in e.array_slots:
+                a = args[k]
+                if a is not out and may_share_bounds(a, out):
+                    return _MISS                     # the slow path copies overlapping inputs
+        ops = e.ops
+        for k in e.array_slots:
+            ops[k].data = args[k].ptr
+        for k, t, weak_t, lo, hi, seen in e.scalar_slots:
+            v = args[k]
+            tv = type(v)
+            sk = (tv, v.hex()) if tv is float else (tv, v) if (tv is int or tv is bool) else None   # hex: -0.0 != 0.0
+            words = seen.get(sk) if sk is not None else None
+            if words is None:
+                words = _scalar_words(v, t, weak_t if not isinstance(v, numpy.generic) else False, lo, hi)
+                if sk is not None:
+                    if len(seen) >= 64:
+                        seen.clear()
+                    seen[sk] = words
+            ops[k].scalar[0] = words[0]
+            ops[k].scalar[1] = words[1]
+        if out is None:
+            out = ndarray._fresh(e.out_shape, e.out_dtype, e.out_strides, e.out_size)
+        ops[e.out_slot].data = out.ptr
+        if _dryrun.enabled:
+            if e.dry is not None:
+                _dryrun.log.append(dict(e.dry))
+            return out
+        st = current_stream_ptr()
+        if e.prebuilt is not None:
+            _lib.check(_lib.lib.b200_ufunc_launch(e.prebuilt, ctypes.byref(e.plan), e.nargs, ops, st))
+        else:
+            _lib.check(_lib.lib.b200_jit_ew_launch_ex(e.handle, ctypes.byref(e.plan), e.nargs, ops, e.threads, 0, None, st))
+        return out
 
     def _get_spec(self, op, has_where):
         key = (op, has_where)

@@ -137,6 +137,9 @@ class _Flags:
             self.c_contiguous, self.f_contiguous, self.owndata)
 
 
+_UFUNCS = {}      # operator name -> ufunc, filled on first use (the routines module imports this one)
+
+
 class ndarray:
     """N-dimensional strided device array (see module docstring)."""
 
@@ -173,6 +176,27 @@ class ndarray:
         self._update_contiguity()
 
     # ---- construction helpers -------------------------------------------------
+    @classmethod
+    def _fresh(cls, shape, dtype, strides, size):
+        """A new C-contiguous array whose metadata the caller already holds (the launcher's memoised
+        call shapes): skips the normalisation of __init__."""
+        self = object.__new__(cls)
+        self.dtype = dtype
+        self._shape = shape
+        self._strides = strides
+        self.size = size
+        nbytes = size * dtype.itemsize
+        if _dryrun.enabled:
+            self._mem = None
+            self.ptr = _dryrun.fake_alloc(nbytes)
+        else:
+            self._mem = torch.empty(nbytes if nbytes > 0 else 1, dtype=torch.uint8, device='cuda')
+            self.ptr = self._mem.data_ptr()
+        self.base = None
+        self._c_contiguous = True
+        self._f_contiguous = _is_f_contiguous(shape, strides, dtype.itemsize)
+        return self
+
     def _update_contiguity(self):
         isz = self.dtype.itemsize
         self._c_contiguous = _is_c_contiguous(self._shape, self._strides, isz)
@@ -584,10 +608,14 @@ class ndarray:
 
     # ---- arithmetic (cupy/_core/core.pyx:1560-1700) ----------------------------------
     def _binop(self, name, other, reflected=False):
-        from cupy_b200._core import _routines_math as m
-        f = getattr(m, name)
-        if isinstance(other, (ndarray, int, float, bool, numpy.generic)) or (
-                isinstance(other, numpy.ndarray) and other.ndim == 0):
+        f = _UFUNCS.get(name)
+        if f is None:
+            from cupy_b200._core import _routines_math as m
+            f = _UFUNCS[name] = getattr(m, name)
+        to = type(other)
+        if (to is ndarray or to is float or to is int or to is bool
+                or isinstance(other, (ndarray, int, float, bool, numpy.generic))
+                or (isinstance(other, numpy.ndarray) and other.ndim == 0)):
             return f(other, self) if reflected else f(self, other)
         return NotImplemented
 

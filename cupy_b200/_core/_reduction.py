@@ -178,6 +178,26 @@ class _AbstractReductionKernel:
     # -- the call ----------------------------------------------------------------------
     def _call(self, in_args, out_args, a_shape, axis, dtype, keepdims, reduce_dims, stream,
               param=0.0):
+        # ---- memoised call shape of the prebuilt route (one dense input, fresh output): everything below depends
+        # only on (dtype, shape, strides, alignment, axis, dtype=, keepdims, param)
+        mkey = None
+        if (len(in_args) == 1 and not out_args and stream is None and type(in_args[0]) is ndarray
+                and self._prebuilt_op is not None and _accelerator.fast_paths_enabled()):
+            a = in_args[0]
+            ax = tuple(axis) if isinstance(axis, list) else axis
+            mkey = (a.dtype, a._shape, a._strides, a.ptr & 15, ax, dtype, bool(keepdims), float(param))
+            memo = _kernel._thread_local.__dict__.setdefault('reduce_memo', {}).setdefault(id(self), {})
+            e = memo.get(mkey)
+            if e is not None:
+                desc, oshape, odtype, ostrides, osize, need, dry = e
+                out = ndarray._fresh(oshape, odtype, ostrides, osize)
+                if _dryrun.enabled:
+                    _dryrun.log.append(dict(dry))
+                    return out
+                st = current_stream_ptr()
+                ws_ptr, ws_bytes = _workspace.get(need, st)
+                _lib.check(_lib.lib.b200_reduce_run(ctypes.byref(desc), a.ptr, out.ptr, ws_ptr, ws_bytes, st))
+                return out
         if dtype is not None:
             dtype = get_dtype(dtype)
         (map_expr, reduce_expr, post_map_expr, in_types, out_types, reduce_type,
@@ -233,20 +253,24 @@ class _AbstractReductionKernel:
                 desc = _lib.ReduceDesc(self._prebuilt_op, layout.kind, _scalar.dtype_id(arrays[0].dtype),
                                        _scalar.dtype_id(target.dtype), layout.batch, layout.n_reduce,
                                        layout.n_out, float(param))
-                if _lib.lib.b200_reduce_supported(ctypes.byref(desc)) and _dryrun.enabled:
-                    _dryrun.record('prebuilt_reduce', name=self.name, layout=layout.kind, batch=layout.batch,
-                                   n_reduce=layout.n_reduce, n_out=layout.n_out)
-                    if target is not out:
-                        _kernel.elementwise_copy(target.reshape(out.shape), out)
-                    return ret
                 if _lib.lib.b200_reduce_supported(ctypes.byref(desc)):
                     need = ctypes.c_size_t()
                     _lib.check(_lib.lib.b200_reduce_workspace_bytes(ctypes.byref(desc), ctypes.byref(need)))
-                    ws_ptr, ws_bytes = _workspace.get(need.value, st)
-                    _lib.check(_lib.lib.b200_reduce_run(ctypes.byref(desc), arrays[0].ptr, target.ptr,
-                                                        ws_ptr, ws_bytes, st))
+                    if _dryrun.enabled:
+                        _dryrun.record('prebuilt_reduce', name=self.name, layout=layout.kind, batch=layout.batch,
+                                       n_reduce=layout.n_reduce, n_out=layout.n_out)
+                    else:
+                        ws_ptr, ws_bytes = _workspace.get(need.value, st)
+                        _lib.check(_lib.lib.b200_reduce_run(ctypes.byref(desc), arrays[0].ptr, target.ptr,
+                                                            ws_ptr, ws_bytes, st))
                     if target is not out:
                         _kernel.elementwise_copy(target.reshape(out.shape), out)
+                    elif mkey is not None and out._c_contiguous and arrays[0] is in_args[0]:
+                        memo = _kernel._thread_local.__dict__.setdefault('reduce_memo', {}).setdefault(id(self), {})
+                        if len(memo) >= 512:
+                            memo.clear()
+                        memo[mkey] = (desc, out._shape, out.dtype, out._strides, out.size, need.value,
+                                      dict(_dryrun.log[-1]) if _dryrun.enabled else None)
                     return ret
             # ---- NVRTC functor on the same skeleton
             if uniform:

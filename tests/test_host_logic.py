@@ -514,3 +514,40 @@ def test_accelerator_switch_and_numpy_dispatch(dry):
     assert isinstance(r, cp.ndarray) and r.shape == (64,)
     with pytest.raises(TypeError):
         np.add(x, np.ones((64, 128), 'f'))                  # no silent host-to-device conversion
+
+
+def test_call_shape_memo_of_the_launcher(dry):
+    """Second and later calls of one call shape take the memoised route: same launch records, fresh outputs,
+    scalar bytes re-encoded, overlapping `out=` falls back to the copying path."""
+    from cupy_b200._core import _kernel
+    a, b = cp.empty((64, 48), 'f'), cp.empty((64, 48), 'f')
+    r1 = cp.add(a, b)
+    first = dict(dry[-1])
+    r2 = cp.add(cp.empty((64, 48), 'f'), b)
+    assert dry[-1] == first and r2.ptr != r1.ptr and r2.shape == (64, 48) and r2.dtype == np.float32
+    memo = _kernel._thread_local.ufunc_memo[id(cp.add)]
+    assert len(memo) >= 1
+    e = next(iter(memo.values()))
+    assert e.ops[e.out_slot].data == r2.ptr                 # the remembered operand block was patched
+    # scalars: value re-encoded per call, -0.0 kept apart from 0.0, NEP 50 overflow still raised
+    cp.multiply(a, 2.0)
+    cp.multiply(a, -0.0)
+    sm = _kernel._thread_local.ufunc_memo[id(cp.multiply)]
+    ent = [v for v in sm.values() if v.scalar_slots][0]
+    k, t, weak, lo, hi, seen = ent.scalar_slots[0]
+    cp.multiply(a, 0.0)
+    assert {key[1] for key in seen} >= {(-0.0).hex(), (0.0).hex()}
+    u8 = cp.empty((16,), np.uint8)
+    u8 + 1
+    with pytest.raises(OverflowError):
+        u8 + 1000
+    # a different alignment class or stride pattern is a different shape
+    n0 = len(memo)
+    cp.add(a[:, ::2], b[:, ::2])
+    assert len(memo) == n0 + 1
+    # reductions
+    a.sum(axis=0)
+    rec = dict(dry[-1])
+    a2 = cp.empty((64, 48), 'f')
+    out = a2.sum(axis=0)
+    assert dry[-1] == rec and out.shape == (48,)

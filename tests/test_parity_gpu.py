@@ -716,3 +716,39 @@ def test_reductions_on_a_non_current_stream_while_another_stream_is_busy(cp):
         st2.synchronize()
     np.testing.assert_allclose(r.get(), a.astype(np.float64).sum(), rtol=1e-5)
     np.testing.assert_allclose(c.get(), m.astype(np.float64).sum(axis=0), rtol=1e-5)
+
+
+def test_memoised_call_shapes_give_the_same_results_as_first_calls(cp):
+    """the launcher remembers a call shape (dtype / shape / strides / alignment -> plan, routing,
+    output metadata) and later calls only patch pointers and scalar bytes.  Repeated calls with new data, new
+    scalar values, `out=`, overlapping `out=` and reductions must match NumPy every time."""
+    rs = np.random.RandomState(33)
+    for rep in range(4):
+        a = rs.rand(257, 33).astype(np.float32)
+        b = rs.rand(257, 33).astype(np.float32)
+        da, db = cp.asarray(a), cp.asarray(b)
+        s = float(rep) + 0.5
+        np.testing.assert_array_equal((da + db).get(), a + b)
+        np.testing.assert_array_equal((da * s + 1).get(), a * np.float32(s) + 1)
+        np.testing.assert_array_equal((da * rep).get(), a * rep)
+        np.testing.assert_array_equal((-0.0 * da).get().view(np.uint32), (np.float32(-0.0) * a).view(np.uint32))
+        np.testing.assert_array_equal((0.0 * da).get().view(np.uint32), (np.float32(0.0) * a).view(np.uint32))
+        o = cp.empty((257, 33), np.float32)
+        cp.add(da, db, out=o)
+        np.testing.assert_array_equal(o.get(), a + b)
+        cp.add(da, db, da)                                   # out aliases an input exactly: in place
+        np.testing.assert_array_equal(da.get(), a + b)
+        flat = cp.asarray(a.reshape(-1))
+        cp.add(flat[:-1], flat[1:], out=flat[1:])            # overlapping, shifted: the input must be copied first
+        want = a.reshape(-1).copy()
+        want[1:] = a.reshape(-1)[:-1] + a.reshape(-1)[1:]
+        np.testing.assert_array_equal(flat.get(), want)
+        np.testing.assert_array_equal(cp.asarray(a.T).T.get(), a)
+        np.testing.assert_allclose(db.sum().get(), b.astype(np.float64).sum(), rtol=1e-5)
+        np.testing.assert_allclose(db.sum(axis=0).get(), b.astype(np.float64).sum(axis=0), rtol=1e-5)
+        np.testing.assert_array_equal(db.argmax(axis=1).get(), b.argmax(axis=1))
+        np.testing.assert_allclose(db.var(axis=1, ddof=rep % 2).get(), b.astype(np.float64).var(axis=1, ddof=rep % 2), rtol=1e-4)
+        ui = cp.asarray(rs.randint(0, 200, 50).astype(np.uint8))
+        with pytest.raises(OverflowError):
+            ui + 300                                          # NEP 50: Python int out of range for uint8, every time
+        np.testing.assert_array_equal((ui + 5).get(), ui.get() + np.uint8(5))
