@@ -362,8 +362,10 @@ def run_ours(args):
         del x, y, z, tx, ty, dx, dy, dz, hx, hy, hz
         torch.cuda.empty_cache()
         c5 = bench_configs.run_c5(world, rank, comm, peak)
+        darr = bench_configs.run_darray_check(world, rank, comm)
         if rank == 0:
             line['c5'] = c5
+            line['darray'] = darr
         if world == 1:
             line['c1_cpu'] = bench_configs.c1_numpy()
             line['configs'], note = bench_configs.run_configs(peak, with_ref_gpu=not args.no_ref_gpu)

@@ -569,3 +569,25 @@ def run_c5(world, rank, comm, peak, log2_total=32, iters=20):
     del x, tx
     torch.cuda.empty_cache()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# DistributedArray over the ranks: sharded rows, lazy SUM-mode reduction, resharding
+# ------------------------------------------------------------------------------------------------
+def run_darray_check(world, rank, comm):
+    import cupy_b200 as cp
+    from cupy_b200.distributed import array as da
+    rows = 64 * world
+    base = np.arange(rows * 96, dtype=np.float32).reshape(rows, 96)
+    imap = {r: slice(64 * r, 64 * (r + 1)) for r in range(world)}
+    d = da.distributed_array(base, imap, da.REPLICA, comm=comm)
+    s = d.sum(axis=0)                                   # one engine kernel per rank, no exchange
+    lazy = s.mode is da.SUM
+    ok = bool(np.allclose(s.get(), base.sum(axis=0), rtol=1e-6))
+    cols = {r: (slice(None), slice(96 * r // world, 96 * (r + 1) // world)) for r in range(world)}
+    t = (d * d).reshard(cols)                           # row shards -> column shards over send / recv
+    ok = ok and bool(np.array_equal(t.get(), base * base))
+    ok = ok and bool(np.array_equal(t.max(axis=1).change_mode(da.REPLICA).get(), (base * base).max(axis=1)))
+    return {'check': 'ok' if ok else 'MISMATCH', 'lazy_sum_mode': lazy, 'ranks': world,
+            'what': 'distributed_array(row shards).sum(axis=0) stays in SUM mode until get(); (d*d).reshard(column '
+                    'shards); max(axis=1).change_mode(REPLICA) -- all compared with NumPy'}

@@ -11,3 +11,6 @@ tcp://host:port) does that plumbing.
 """
 from cupy_b200.distributed._comm import (  # noqa: F401
     NCCLBackend, init_process_group, sharded_sum, sharded_var, combine_moments)
+from cupy_b200.distributed import array  # noqa: F401,E402
+from cupy_b200.distributed.array import (  # noqa: F401,E402
+    DistributedArray, distributed_array, make_2d_index_map, REPLICA, MIN, MAX, SUM, PROD)
