@@ -585,6 +585,8 @@ class ElementwiseKernel:
         memo[fkey] = e
 
     def _fast_launch(self, e, args):
+        if _dryrun.enabled and e.dry is None:
+            return _MISS
         ops = e.ops
         if e.empty:
             outs = [ndarray._fresh(sh, dt, st, sz) for dt, sh, st, sz in e.out_dtype]
@@ -1037,6 +1039,8 @@ class ufunc:
 
     def _fast_launch(self, e, args, out):
         """A call whose shape has been seen: patch pointers and scalar bytes into the remembered operand block."""
+        if _dryrun.enabled and e.dry is None:
+            return _MISS                         # remembered on a live run: the dry run records through the full path
         if out is not None:
             for k in e.array_slots:
                 a = args[k]

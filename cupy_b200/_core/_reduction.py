@@ -188,7 +188,7 @@ class _AbstractReductionKernel:
             mkey = (a.dtype, a._shape, a._strides, a.ptr & 15, ax, dtype, bool(keepdims), float(param))
             memo = _kernel._thread_local.__dict__.setdefault('reduce_memo', {}).setdefault(id(self), {})
             e = memo.get(mkey)
-            if e is not None:
+            if e is not None and not (_dryrun.enabled and e[6] is None):
                 desc, oshape, odtype, ostrides, osize, need, dry = e
                 out = ndarray._fresh(oshape, odtype, ostrides, osize)
                 if _dryrun.enabled:

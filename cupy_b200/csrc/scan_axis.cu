@@ -15,9 +15,12 @@
 //       walks down n with U rows of loads in flight; a warp instruction reads 32*V adjacent
 //       elements of one row, so every access is a full line; the running sums stay in registers.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 #include "include/b200/scan.cuh"
+#include "include/b200/scan_march.cuh"
+#include "tma_host.h"
 #include "scan_table.h"
 
 namespace b200 {
@@ -162,6 +165,54 @@ __global__ void __launch_bounds__(256) scan_cols_kernel(const In* __restrict__ x
     }
 }
 
+// ---- the column-march kernel (b200/scan_march.cuh): one persistent block per column strip, TMA-pipelined --------
+template <class Cfg, class Op>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) scan_march_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                                    const __grid_constant__ CUtensorMap tm_out,
+                                                                    int64_t outer, int64_t n, int64_t inner) {
+    scan_march_body<Cfg, Op>(&tm_in, &tm_out, outer, n, inner);
+}
+
+template <class T, class Op, int W_BYTES>
+static int launch_march(const T* x, T* y, int64_t outer, int64_t n, int64_t inner, int sm_count, cudaStream_t s) {
+    typedef ScanMarchCfg<T, W_BYTES, 4, 2> Cfg;
+    auto kern = scan_march_kernel<Cfg, Op>;
+    static bool attr_set = false;       // per instantiation; benign race
+    if (!attr_set) {
+        B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_set = true;
+    }
+    CUtensorMap tin, tout;
+    const uint64_t dims[3] = {uint64_t(inner), uint64_t(n), uint64_t(outer)};
+    const uint64_t strides[2] = {uint64_t(inner) * sizeof(T), uint64_t(n) * uint64_t(inner) * sizeof(T)};
+    const uint32_t box[3] = {uint32_t(Cfg::W), uint32_t(Cfg::R), 1u};
+    int st = make_tensor_map(&tin, sizeof(T), x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (st) return st;
+    st = make_tensor_map(&tout, sizeof(T), y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (st) return st;
+    const int64_t insts = outer * ((inner + Cfg::W - 1) / Cfg::W);
+    const unsigned grid = unsigned(std::min<int64_t>(insts, sm_count));
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tin, tout, outer, n, inner);
+    B200_CUDA_TRY(cudaPeekAtLastError());
+    return 0;
+}
+
+// Strip width for the march: the widest of 512 / 256 / 128 bytes that still gives (nearly) one strip per SM; 0 when
+// even 128-byte strips leave more than half of the SMs idle (narrow matrices keep the split scheme).
+static int march_width(int64_t outer, int64_t inner_bytes, int sm_count) {
+    const int widths[3] = {512, 256, 128};
+    for (int w : widths)
+        if (outer * ((inner_bytes + w - 1) / w) * 5 >= int64_t(sm_count) * 4) return w;
+    return (outer * ((inner_bytes + 127) / 128) * 2 >= sm_count) ? 128 : 0;
+}
+
+template <class In, class Acc, class Out> struct march_eligible { static constexpr bool value = false; };
+template <> struct march_eligible<float, float, float> { static constexpr bool value = true; };
+template <> struct march_eligible<double, double, double> { static constexpr bool value = true; };
+template <> struct march_eligible<int32_t, int32_t, int32_t> { static constexpr bool value = true; };
+template <> struct march_eligible<long long, long long, long long> { static constexpr bool value = true; };
+template <> struct march_eligible<unsigned long long, unsigned long long, unsigned long long> { static constexpr bool value = true; };
+
 // segments to cut n into so that outer * S * inner / V threads fill the GPU (1 = no split)
 static int64_t axis_split(int64_t outer, int64_t n, int64_t inner, int sm_count) {
     if (inner <= 1) return 1;
@@ -214,6 +265,16 @@ static int run_axis(const void* xv, void* yv, int64_t outer, int64_t n, int64_t 
         const int64_t cols = outer * S * (vec ? inner / V : inner);
         const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>((cols + 255) / 256, int64_t(sm_count) * 8)));
         Acc* tot = static_cast<Acc*>(ws);
+        if constexpr (march_eligible<In, Acc, Out>::value) {
+            static const bool force_split = getenv("B200_SCAN_AXIS_SPLIT") != nullptr;      // A/B knob: the two-read scheme
+            const int64_t inner_bytes = inner * int64_t(sizeof(In));
+            const int wb = (S > 1 && !force_split && inner_bytes % 16 == 0 && xa % 16 == 0 && ya % 16 == 0 &&
+                            inner < (int64_t(1) << 31) && n < (int64_t(1) << 31) && outer < (int64_t(1) << 31))
+                               ? march_width(outer, inner_bytes, sm_count) : 0;
+            if (wb == 512) return launch_march<In, Op, 512>(x, y, outer, n, inner, sm_count, s);
+            if (wb == 256) return launch_march<In, Op, 256>(x, y, outer, n, inner, sm_count, s);
+            if (wb == 128) return launch_march<In, Op, 128>(x, y, outer, n, inner, sm_count, s);
+        }
         if (S > 1) {
             if (ws_bytes < size_t(outer * S * inner) * sizeof(Acc) || !ws)
                 return fail(B200_E_WORKSPACE, "scan_axis workspace %zu < %zu", ws_bytes, size_t(outer * S * inner) * sizeof(Acc));

@@ -118,3 +118,35 @@ def test_large_axis_scans(cp):
     d = cp.asarray(a)
     np.testing.assert_array_equal(d.cumsum(axis=1).get(), a.cumsum(axis=1))
     np.testing.assert_array_equal(d.cumsum(axis=0).get(), a.cumsum(axis=0))
+
+
+# shapes that take the column-march kernel (csrc/include/b200/scan_march.cuh): a few thousand to ~150 thousand column
+# vectors, scanned axis not last; ragged row tiles (n % R != 0), ragged strips (inner % W != 0), several outer slices,
+# every strip width (512 / 256 / 128 bytes per row)
+MARCH_SHAPES = [(700, 16384), (1030, 4096), (300, 9000), (513, 2052), (3, 600, 4100), (2, 2049, 1540), (260, 40000)]
+
+
+@pytest.mark.parametrize('dt', ['int64', 'int32', 'uint64', 'float32', 'float64'])
+@pytest.mark.parametrize('shape', MARCH_SHAPES)
+def test_column_march_scans(cp, shape, dt):
+    a = rnd(shape, dt)
+    d = cp.asarray(a)
+    ax = len(shape) - 2
+    got = d.cumsum(axis=ax).get()
+    if np.dtype(dt).kind == 'f':
+        want = a.astype(np.float64).cumsum(axis=ax)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-3 if dt == 'float32' else 1e-10)
+    else:
+        np.testing.assert_array_equal(got, a.cumsum(axis=ax))
+    # cumprod: rows / columns past the edge of a tile must count as ones, not as the zeros TMA fills in
+    p = np.where(RS.rand(*shape) < 0.002, 2, 1).astype(dt)
+    got = cp.asarray(p).cumprod(axis=ax).get()
+    want = p.cumprod(axis=ax)
+    if np.dtype(dt).kind == 'f':
+        np.testing.assert_allclose(got, want, rtol=1e-6)
+    else:
+        np.testing.assert_array_equal(got, want)
+    # in place (out= the input itself)
+    d2 = cp.asarray(a)
+    cp.cumsum(d2, axis=ax, out=d2)
+    np.testing.assert_array_equal(d2.get(), got if False else d.cumsum(axis=ax).get())
