@@ -20,6 +20,7 @@ string is wrapped in the tiler glue of `_codegen.py` and compiled by NVRTC.
 from __future__ import annotations
 
 import ctypes
+import os as _os
 import re as _re
 import string
 import threading
@@ -331,7 +332,21 @@ def _prebuilt_fits(plan, ops, args):
 
 
 # tunables of the generated kernels (bench/tuning scripts override these)
-tunables = {
+class _Tunables(dict):
+    """A/B knobs; changing one invalidates the memoised call shapes (they hold plans made under the old value)."""
+
+    def __setitem__(self, key, value):
+        dict.__setitem__(self, key, value)
+        clear_call_shape_memo()
+
+
+def clear_call_shape_memo():
+    global _memo_epoch
+    _memo_epoch += 1
+
+
+_memo_epoch = 0
+tunables = _Tunables({
     'threads': 256,
     'flat_unroll': 4,
     'row_unroll': 2,
@@ -339,7 +354,7 @@ tunables = {
     'tma_stages': 0,          # TILED_TMA ring depth, 0 = library default
     'reg_unroll': 0,          # TILED_REG blocks per thread, 0 = library default (8 vector loads in flight)
     'reg_min_blocks': 0,      # TILED_REG __launch_bounds__ min blocks/SM, 0 = from the register estimate
-}
+})
 
 
 def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stream=None, ind_shape=None):
@@ -824,6 +839,9 @@ def _fast_key(args, out):
         if type(out) is not ndarray:
             return None
         key.append((out.dtype, out._shape, out._strides, out.ptr & 15, 'out'))
+    # plans depend on the A/B knobs: the tunables (epoch) and the planner's environment switch
+    key.append(_memo_epoch)
+    key.append(_os.environ.get('B200_EW_TILED_MODE'))
     return tuple(key)
 
 
