@@ -223,9 +223,14 @@ __device__ __forceinline__ void scan_pipe_body(const void* tm_in, const void* tm
                 Acc tsum = ident;
                 if constexpr (Cfg::HOLD_RAW) {
                     const In* e = reinterpret_cast<const In*>(raw[SET]);
+                    if (__builtin_expect(!ragged, 1)) {          // no per-item predicates on the streaming path
 #pragma unroll
-                    for (int j = 0; j < IPT; ++j)
-                        if (!ragged || g0 + j < n_main) tsum = Op::combine(tsum, PipeCvt<In, Acc>::in(e[j]));
+                        for (int j = 0; j < IPT; ++j) tsum = Op::combine(tsum, PipeCvt<In, Acc>::in(e[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < IPT; ++j)
+                            if (g0 + j < n_main) tsum = Op::combine(tsum, PipeCvt<In, Acc>::in(e[j]));
+                    }
                 } else {
                     Acc* v = reinterpret_cast<Acc*>(raw[SET]);      // In == Acc == Out: scan in place
                     if (__builtin_expect(ragged, 0)) {
@@ -301,12 +306,21 @@ __device__ __forceinline__ void scan_pipe_body(const void* tm_in, const void* tm
             Out o[IPT];
             if constexpr (Cfg::HOLD_RAW) {
                 const In* e = reinterpret_cast<const In*>(raw[OLD]);
+                if (__builtin_expect(!ragged, 1)) {
 #pragma unroll
-                for (int j = 0; j < IPT; ++j) {
-                    const Acc v = PipeCvt<In, Acc>::in(e[j]);
-                    if (MODE == 2) acc = v;
-                    else if (!ragged || g0 + j < n_main) acc = Op::combine(acc, v);
-                    o[j] = static_cast<Out>(acc);
+                    for (int j = 0; j < IPT; ++j) {
+                        const Acc v = PipeCvt<In, Acc>::in(e[j]);
+                        acc = MODE == 2 ? v : Op::combine(acc, v);
+                        o[j] = static_cast<Out>(acc);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < IPT; ++j) {
+                        const Acc v = PipeCvt<In, Acc>::in(e[j]);
+                        if (MODE == 2) acc = v;
+                        else if (g0 + j < n_main) acc = Op::combine(acc, v);
+                        o[j] = static_cast<Out>(acc);
+                    }
                 }
             } else {
                 const Acc* v = reinterpret_cast<const Acc*>(raw[OLD]);
