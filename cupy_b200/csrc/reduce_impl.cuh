@@ -87,6 +87,8 @@ static int full_blocks_per_sm() {
         if constexpr (SHARDED) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, reduce_full_sharded_kernel<Op, VEC, UNROLL>, kRedThreads, 0);
         else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, reduce_full_kernel<Op, VEC, UNROLL>, kRedThreads, 0);
         occ = (e == cudaSuccess && o > 0) ? std::min(o, 8) : 8;
+        static const int forced = [] { const char* v = getenv("B200_FULL_BLOCKS_PER_SM"); return v ? atoi(v) : 0; }();   // A/B knob
+        if (forced > 0 && forced < occ) occ = forced;
     }
     return occ;
 }
@@ -176,7 +178,10 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
         acc_t* partials = reinterpret_cast<acc_t*>(static_cast<char*>(ws) + kTicketBytes);
         if constexpr (peer_exchangeable<Op>::value && !Op::kWideIndex && sizeof(acc_t) <= 4 * kExWords) {
             if (ex.nranks > 1) {
-                const int bps = fullvec ? full_blocks_per_sm<Op, FULLVEC, U, true>() : full_blocks_per_sm<Op, 1, U, true>();
+                // never more resident blocks than the plain instantiation runs with: the sharded one needs fewer
+                // registers, but a sixth block per SM costs the moments kernel 11 us at 2^29 (profiles/r02_sharded_probe.log)
+                const int bps = fullvec ? std::min(full_blocks_per_sm<Op, FULLVEC, U, true>(), full_blocks_per_sm<Op, FULLVEC, U, false>())
+                                        : std::min(full_blocks_per_sm<Op, 1, U, true>(), full_blocks_per_sm<Op, 1, U, false>());
                 const int grid = full_grid(d->n_reduce, fullvec ? FULLVEC : 1, U, di.sm_count, bps);
                 if (grid > 1 && ws_bytes < kTicketBytes + partial_bytes)
                     return fail(B200_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, kTicketBytes + partial_bytes);
