@@ -463,7 +463,12 @@ def _c3_ref(e, refjit, refcub, t, op, ax, sfx, m, isz, nb, alloc, it):
              ('; accumulates in __half' if sfx == 'f16' and op == 'sum' else ''), it)
         return
     if op == 'argmax' and ax == 1:
-        e['ref_gpu'] = {'skipped': 'reference uses its CUB-block JIT template (_cub_reduction.pyx:67-215); not rendered'}
+        y = torch.empty(m, device='cuda', dtype=torch.int64)
+        f = refjit.cub_block('ref_cub_argmax_' + sfx, ptr, y.data_ptr(), m, m)
+        _ref(e, nb, f, 'reference CUB-block JIT template (_cub_reduction.pyx:33-242): one 512-thread block per row, '
+                       '4 items per thread, BlockReduce per 2048-element tile', it)
+        f()
+        e['ref_gpu']['same_indices'] = bool(torch.equal(y, torch.argmax(t, dim=1))) or 'ties differ from torch.argmax'
         return
     if op in ('sum', 'max', 'argmax'):       # axis=0: generic reduction, 1-D collapsed input
         odt = torch.int64 if op == 'argmax' else tdt

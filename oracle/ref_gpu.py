@@ -3,7 +3,8 @@
 GPU-side harness for the REFERENCE's own kernels, used by bench.py's `reference_gpu` leg and by the
 GPU parity tests: it launches
   * the cubins rendered from the reference's JIT templates by oracle/render_ref_jit.py
-    (oracle/_ref/jit/*.cubin + manifest.json) with the reference's launch geometry
+    (oracle/_ref/jit/*.cubin + manifest.json: elementwise, generic reduction, CUB-block reduction) with the
+    reference's launch geometry
     (`linear_launch` cupy/cuda/function.pyx:153-171, `_get_block_specs` cupy/_core/_reduction.pyx:239-253,
     `_launch` :481-508), through libcuda (cuModuleLoadData / cuLaunchKernel, what
     cupy_backends/cuda/api/driver.pyx:273-286 calls), and
@@ -129,6 +130,14 @@ class RefJit:
         launch = self.prepare(name, args, out_block_num, block_size, stream)
         launch.geometry = {'block_size': block_size, 'block_stride': block_stride, 'grid': out_block_num}
         return launch
+
+
+    def cub_block(self, name, in_ptr, out_ptr, n_segments, segment_size, stream=0):
+        """_launch_cub, one-pass branch (cupy/_core/_cub_reduction.pyx:545-563): one block per segment,
+        linear_launch(out_block_num * block_size, ..., block_size)."""
+        block = self.manifest[name]['block_size']
+        args = [c_void_p(in_ptr), c_void_p(out_ptr), ctypes.c_int32(segment_size), ctypes.c_int32(0)]
+        return self.prepare(name, args, n_segments, block, stream)
 
 
 class RefCub:

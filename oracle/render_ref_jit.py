@@ -24,6 +24,7 @@ What is rendered (reference file:line of each template / routine):
                               `block_specs` below), `linear_launch` cupy/cuda/function.pyx:153-171
   min/max/argmax preamble     cupy/_core/_routines_statistics.pyx:190-276
   var second pass             cupy/_core/_routines_statistics.pyx:603-625 (`_var_core_float32/16`)
+  CUB-block JIT reduction     cupy/_core/_cub_reduction.pyx:33-242 (argmax along the contiguous axis)
 """
 from __future__ import annotations
 
@@ -72,6 +73,10 @@ def cindexer(ndim, idx32=True):
     return {'kind': 'cindexer', 'ctype': 'CIndexer<%d, %d>' % (ndim, int(idx32)), 'ndim': ndim}
 
 
+def pointer(const=False):
+    return {'kind': 'pointer', 'ctype': 'const void*' if const else 'void*'}
+
+
 def scalar(t):
     return {'kind': 'scalar', 'ctype': CTYPE[t], 'np': {'f': 'float32', 'i': 'int32', 'd': 'float64'}[t]}
 
@@ -108,8 +113,28 @@ def reduction_source(tpl, name, typedefs, params, block_size, reduce_type, ident
         input_expr=input_expr, output_expr=output_expr)
 
 
+def cub_block_source(cpyx, name, typedefs, params, block_size, items_per_thread, reduce_type, identity, pre_map,
+                     reduce_expr, post_map, preamble=''):
+    """_create_cub_reduction_function (cupy/_core/_cub_reduction.pyx:33-242): the module text is assembled from
+    the literals of that function, in order, with the `pre_map_expr == 'in0'` alternatives chosen as it does."""
+    at = cpyx.index('cdef function.Function _create_cub_reduction_function')
+    end = cpyx.index('type_decls = set()', at)
+    lits = re.findall(r"'''(.*?)'''", cpyx[at:end], re.S)
+    assert len(lits) == 6, len(lits)
+    head, load_t, body, load_in0, load_map, tail = lits
+    hdr = re.search(r"_cub_path == '<bundle>':\s*_cub_header = '''(.*?)'''", cpyx, re.S).group(1)
+    code = hdr + head + (load_t if pre_map == 'in0' else '') + body + (load_in0 if pre_map == 'in0' else load_map) + tail
+    plist = ', '.join('%s %s' % (p['ctype'], n) for n, p in params)
+    return HEADERS + string.Template(code).substitute(
+        name=name, block_size=block_size, items_per_thread=items_per_thread, reduce_type=reduce_type, params=plist,
+        type_decls=_type_decls(typedefs), identity=identity, reduce_expr=reduce_expr, pre_map_expr=pre_map,
+        post_map_expr=post_map, type_preamble=''.join('typedef %s %s;\n' % (CTYPE[c], t) for t, c in typedefs),
+        preamble=preamble)
+
+
 def kernels():
     kpyx = _read('cupy/_core/_kernel.pyx')
+    cpyx = _read('cupy/_core/_cub_reduction.pyx')
     rpyx = _read('cupy/_core/_reduction.pyx')
     spyx = _read('cupy/_core/_routines_statistics.pyx')
     ew_tpl = _template_after(kpyx, 'cdef str _get_simple_elementwise_kernel_code')
@@ -171,6 +196,17 @@ def kernels():
         simple('ref_max_' + sfx, t, t, idx32, mm + '(in0)', 'my_max_float(a, b)', 'out0 = a.value', mm, '', minmax)
         simple('ref_argmax_' + sfx, t, 'q', idx32, mm + '(in0, _J)', 'my_argmax_float(a, b)', 'out0 = a.index',
                mm, '', minmax)
+
+    # ---- CUB-block JIT path (_cub_reduction.pyx): argmax along the contiguous axis, one 512-thread block per row,
+    #      4 items per thread (_get_cub_block_specs :391-410); args: raw pointers + int32 segment / array size (:657-664)
+    for t, sfx in (('f', 'f32'), ('e', 'f16')):
+        name = 'ref_cub_argmax_' + sfx
+        params = [('_raw_in0', pointer(True)), ('_raw_out0', pointer()),
+                  ('_segment_size', dict(scalar('i'), ctype='const int')), ('_array_size', dict(scalar('i'), ctype='const int'))]
+        typedefs = [('type_in0_raw', t), ('type_out0_raw', 'q'), ('IndexT', 'i'), ('sizeT', 'i')]
+        out.append(dict(name=name, family='cub_block', block_size=512, params=params,
+                        source=cub_block_source(cpyx, name, typedefs, params, 512, 4, mm, '', mm + '(in0, _J)',
+                                                'my_argmax_float(a, b)', 'out0 = a.index', minmax)))
 
     # ---- var second pass: ReductionKernel('S x, T mean, float32 alpha', 'float32 out', 'my_norm(x - mean)', ...)
     #      x and the broadcast keepdims mean stay 2-D (_reduced_view_core leaves 2-D non-contiguous sets alone,
