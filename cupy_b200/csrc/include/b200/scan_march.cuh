@@ -3,7 +3,8 @@
 // (scan_cols), too many rows to waste a second read on segment totals (the split scheme, 12 B / float32).
 //
 // The columns are cut into strips of W_BYTES (128 / 256 / 512 bytes per row, so that there are about as many
-// strips as SMs); ONE persistent 512-thread block marches down each strip, tile by tile (R rows x W_BYTES),
+// strips as SMs; the width is that of the wider of input and result, so casting scans -- int32 -> int64,
+// bool -> int64, float16 with a float accumulator -- run here too); ONE persistent 512-thread block marches down each strip, tile by tile (R rows x W_BYTES),
 // carrying the running column sums in registers.  Nothing is exchanged between blocks: the parallelism is
 // across strips, the bytes in flight come from the TMA ring (input tiles of 32 KB, 4 stages deep, one tensor
 // copy each; output tiles leave through a second ring by TMA stores).  A warp owns RW * RPT consecutive rows of
@@ -17,27 +18,56 @@
 
 namespace b200 {
 
-template <class T, int W_BYTES_, int SI_, int SO_>
+template <class In, class Acc, class Out, int W_BYTES_, int SI_, int SO_>
 struct ScanMarchCfg {
-    typedef T elem_t;
+    typedef In in_t; typedef Acc acc_t; typedef Out out_t;
     static constexpr int THREADS = 512, NWARPS = 16, RPT = 4;
-    static constexpr int W_BYTES = W_BYTES_;                 // bytes of a tile row: 128, 256 or 512
+    static constexpr int SWIDE = int(sizeof(In) > sizeof(Out) ? sizeof(In) : sizeof(Out));
+    static constexpr int W_BYTES = W_BYTES_;                 // bytes of a tile row on its WIDER side: 128, 256 or 512
     static constexpr int LPR = W_BYTES / 16;                 // lanes per row: 8, 16, 32
     static constexpr int RW = 32 / LPR;                      // rows a warp covers per load instruction: 4, 2, 1
     static constexpr int R = NWARPS * RW * RPT;              // tile rows: 256, 128, 64
-    static constexpr int W = W_BYTES / int(sizeof(T));       // tile columns
-    static constexpr int V = 16 / int(sizeof(T));            // columns per lane
-    static constexpr int STAGE = R * W_BYTES;                // 32 KB
+    static constexpr int V = 16 / SWIDE;                     // columns per lane (16 bytes of the wider type)
+    static constexpr int W = LPR * V;                        // tile columns
+    static constexpr int IN_LANE = V * int(sizeof(In)), OUT_LANE = V * int(sizeof(Out));   // bytes a lane reads / writes per row
+    static constexpr int IN_ROW = W * int(sizeof(In)), OUT_ROW = W * int(sizeof(Out));
+    static constexpr int IN_STAGE = R * IN_ROW, OUT_STAGE = R * OUT_ROW;
     static constexpr int SI = SI_, SO = SO_;
-    static constexpr int SMEM = 1024 + (SI + SO) * STAGE + 8 * SI;
+    static constexpr int SMEM = 1024 + SI * ((IN_STAGE + 1023) / 1024 * 1024) + SO * OUT_STAGE + 8 * SI;
+    static constexpr int IN_PITCH = (IN_STAGE + 1023) / 1024 * 1024;     // stage pitch (TMA destinations stay 128-byte aligned)
     static_assert(W_BYTES == 128 || W_BYTES == 256 || W_BYTES == 512, "strip width");
-    static_assert(STAGE == 32768 && R <= 256 && W <= 256, "TMA box");
+    static_assert(R <= 256 && W <= 256 && IN_ROW % 16 == 0 && OUT_ROW % 16 == 0, "TMA box");
+    static_assert(IN_LANE == 16 || IN_LANE == 8 || IN_LANE == 4 || IN_LANE == 2, "lane load width");
+};
+
+template <int BYTES> struct MarchLoad;
+template <> struct MarchLoad<16> {
+    B200_DEVICE static void ld(uint32_t addr, void* dst) { *reinterpret_cast<uint4*>(dst) = ld_shared_v4(addr); }
+};
+template <> struct MarchLoad<8> {
+    B200_DEVICE static void ld(uint32_t addr, void* dst) { *reinterpret_cast<uint2*>(dst) = ld_shared_v2(addr); }
+};
+template <> struct MarchLoad<4> {
+    B200_DEVICE static void ld(uint32_t addr, void* dst) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+        *reinterpret_cast<uint32_t*>(dst) = v;
+    }
+};
+template <> struct MarchLoad<2> {
+    B200_DEVICE static void ld(uint32_t addr, void* dst) {
+        uint16_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+        *reinterpret_cast<uint16_t*>(dst) = v;
+    }
 };
 
 template <class Cfg, class Op>
 __device__ __forceinline__ void scan_march_body(const void* tm_in, const void* tm_out, int64_t outer, int64_t n,
                                                 int64_t inner) {
-    typedef typename Cfg::elem_t T;
+    typedef typename Cfg::in_t In;
+    typedef typename Cfg::acc_t T;                          // accumulator; the tile is converted on load
+    typedef typename Cfg::out_t Out;
     constexpr int THREADS = Cfg::THREADS, NWARPS = Cfg::NWARPS, RPT = Cfg::RPT, LPR = Cfg::LPR, RW = Cfg::RW;
     constexpr int V = Cfg::V, W = Cfg::W, R = Cfg::R, SI = Cfg::SI, SO = Cfg::SO;
 
@@ -45,7 +75,7 @@ __device__ __forceinline__ void scan_march_body(const void* tm_in, const void* t
     __shared__ __align__(16) T wslab[NWARPS][W];            // per-warp column totals of the current tile
     __shared__ __align__(16) T tile_tot[W];                 // column totals of the whole tile
     const uint32_t base = (smem_u32(march_smem_raw) + 1023u) & ~1023u;
-    const uint32_t in0 = base, out0 = base + SI * Cfg::STAGE, bar0 = out0 + SO * Cfg::STAGE;
+    const uint32_t in0 = base, out0 = base + SI * Cfg::IN_PITCH, bar0 = out0 + SO * Cfg::OUT_STAGE;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = lane % LPR, rg = lane / LPR;               // 16-byte column chunk, row group inside the warp
@@ -70,10 +100,10 @@ __device__ __forceinline__ void scan_march_body(const void* tm_in, const void* t
             int64_t o, strip, seg;
             coords(t, o, strip, seg);
             const int s = int(t % SI);
-            mbar_expect_tx_a(bar0 + 8 * s, Cfg::STAGE);
+            mbar_expect_tx_a(bar0 + 8 * s, Cfg::IN_STAGE);
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                ::"r"(in0 + s * Cfg::STAGE), "l"(tm_in), "r"(int32_t(strip * W)), "r"(int32_t(seg * R)), "r"(int32_t(o)),
+                ::"r"(in0 + s * Cfg::IN_PITCH), "l"(tm_in), "r"(int32_t(strip * W)), "r"(int32_t(seg * R)), "r"(int32_t(o)),
                   "r"(bar0 + 8 * s) : "memory");
         }
     };
@@ -94,7 +124,8 @@ __device__ __forceinline__ void scan_march_body(const void* tm_in, const void* t
     T running[V];                                            // column sums of all tiles above the current one
 #pragma unroll
     for (int k = 0; k < V; ++k) running[k] = ident;
-    const uint32_t my_off = uint32_t((warp * RW * RPT + rg * RPT) * Cfg::W_BYTES + c * 16);   // first of my RPT rows
+    const uint32_t my_row = uint32_t(warp * RW * RPT + rg * RPT);                             // first of my RPT rows
+    const uint32_t my_in = my_row * Cfg::IN_ROW + c * Cfg::IN_LANE, my_out = my_row * Cfg::OUT_ROW + c * Cfg::OUT_LANE;
 
     for (int64_t t = 0; t < my_tiles; ++t) {
         int64_t o, strip, seg;
@@ -105,14 +136,14 @@ __device__ __forceinline__ void scan_march_body(const void* tm_in, const void* t
         }
         const int s = int(t % SI);
         mbar_wait_a(bar0 + 8 * s, uint32_t((t / SI) & 1));
-        const uint32_t st = in0 + s * Cfg::STAGE + my_off;
+        const uint32_t st = in0 + s * Cfg::IN_PITCH + my_in;
         T a[RPT][V];
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
-            const uint4 v = ld_shared_v4(st + r * Cfg::W_BYTES);
-            const T* e = reinterpret_cast<const T*>(&v);
+            In e[V];
+            MarchLoad<Cfg::IN_LANE>::ld(st + r * Cfg::IN_ROW, e);
 #pragma unroll
-            for (int k = 0; k < V; ++k) a[r][k] = e[k];
+            for (int k = 0; k < V; ++k) a[r][k] = PipeCvt<In, T>::in(e[k]);
         }
         // rows past n and columns past inner were zero-filled by TMA: cumprod needs ones there (the stores are clipped)
         const int64_t row0 = seg * R + (warp * RW * RPT + rg * RPT);
@@ -155,10 +186,8 @@ __device__ __forceinline__ void scan_march_body(const void* tm_in, const void* t
 #pragma unroll
         for (int w = 0; w < NWARPS - 1; ++w) {
             if (w < warp) {
-                const uint4 q = *reinterpret_cast<const uint4*>(&wslab[w][c * V]);
-                const T* e = reinterpret_cast<const T*>(&q);
 #pragma unroll
-                for (int k = 0; k < V; ++k) before[k] = Op::combine(before[k], e[k]);
+                for (int k = 0; k < V; ++k) before[k] = Op::combine(before[k], wslab[w][c * V + k]);
             }
         }
         if (warp == NWARPS - 1 && rg == RW - 1) {
@@ -168,13 +197,19 @@ __device__ __forceinline__ void scan_march_body(const void* tm_in, const void* t
         T pre[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) pre[k] = Op::combine(running[k], Op::combine(before[k], excl[k]));
-        const uint32_t so = out0 + uint32_t(t % SO) * Cfg::STAGE + my_off;
+        const uint32_t so = out0 + uint32_t(t % SO) * Cfg::OUT_STAGE + my_out;
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
-            T o4[V];
+            Out o4[V];
 #pragma unroll
-            for (int k = 0; k < V; ++k) o4[k] = Op::combine(pre[k], a[r][k]);
-            st_shared_v4(so + r * Cfg::W_BYTES, *reinterpret_cast<const uint4*>(o4));
+            for (int k = 0; k < V; ++k) o4[k] = static_cast<Out>(Op::combine(pre[k], a[r][k]));
+            if constexpr (Cfg::OUT_LANE == 16) {
+                st_shared_v4(so + r * Cfg::OUT_ROW, *reinterpret_cast<const uint4*>(o4));
+            } else {
+                static_assert(Cfg::OUT_LANE == 8, "a lane writes 16 bytes, or 8 when the input is the wider side");
+                const uint2 q = *reinterpret_cast<const uint2*>(o4);
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(so + r * Cfg::OUT_ROW), "r"(q.x), "r"(q.y) : "memory");
+            }
         }
         fence_proxy_async_smem();
         __syncthreads();                                                         // (C)
@@ -182,16 +217,12 @@ __device__ __forceinline__ void scan_march_body(const void* tm_in, const void* t
             asm volatile(
                 "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
                 ::"l"(tm_out), "r"(int32_t(strip * W)), "r"(int32_t(seg * R)), "r"(int32_t(o)),
-                  "r"(out0 + uint32_t(t % SO) * Cfg::STAGE) : "memory");
+                  "r"(out0 + uint32_t(t % SO) * Cfg::OUT_STAGE) : "memory");
             tma_commit_group();
             tma_wait_group_read<SO - 1>();
         }
-        {
-            const uint4 q = *reinterpret_cast<const uint4*>(&tile_tot[c * V]);
-            const T* e = reinterpret_cast<const T*>(&q);
 #pragma unroll
-            for (int k = 0; k < V; ++k) running[k] = Op::combine(running[k], e[k]);
-        }
+        for (int k = 0; k < V; ++k) running[k] = Op::combine(running[k], tile_tot[c * V + k]);
     }
     if (dma) tma_wait_group<0>();
 }

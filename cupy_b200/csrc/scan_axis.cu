@@ -173,9 +173,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) scan_march_kernel(const __gri
     scan_march_body<Cfg, Op>(&tm_in, &tm_out, outer, n, inner);
 }
 
-template <class T, class Op, int W_BYTES>
-static int launch_march(const T* x, T* y, int64_t outer, int64_t n, int64_t inner, int sm_count, cudaStream_t s) {
-    typedef ScanMarchCfg<T, W_BYTES, 4, 2> Cfg;
+template <class In, class Acc, class Out, class Op, int W_BYTES>
+static int launch_march(const In* x, Out* y, int64_t outer, int64_t n, int64_t inner, int sm_count, cudaStream_t s) {
+    typedef ScanMarchCfg<In, Acc, Out, W_BYTES, 4, 2> Cfg;
     auto kern = scan_march_kernel<Cfg, Op>;
     static bool attr_set = false;       // per instantiation; benign race
     if (!attr_set) {
@@ -184,11 +184,12 @@ static int launch_march(const T* x, T* y, int64_t outer, int64_t n, int64_t inne
     }
     CUtensorMap tin, tout;
     const uint64_t dims[3] = {uint64_t(inner), uint64_t(n), uint64_t(outer)};
-    const uint64_t strides[2] = {uint64_t(inner) * sizeof(T), uint64_t(n) * uint64_t(inner) * sizeof(T)};
+    const uint64_t sin[2] = {uint64_t(inner) * sizeof(In), uint64_t(n) * uint64_t(inner) * sizeof(In)};
+    const uint64_t sout[2] = {uint64_t(inner) * sizeof(Out), uint64_t(n) * uint64_t(inner) * sizeof(Out)};
     const uint32_t box[3] = {uint32_t(Cfg::W), uint32_t(Cfg::R), 1u};
-    int st = make_tensor_map(&tin, sizeof(T), x, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    int st = make_tensor_map(&tin, sizeof(In), x, 3, dims, sin, box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (st) return st;
-    st = make_tensor_map(&tout, sizeof(T), y, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    st = make_tensor_map(&tout, sizeof(Out), y, 3, dims, sout, box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (st) return st;
     const int64_t insts = outer * ((inner + Cfg::W - 1) / Cfg::W);
     const unsigned grid = unsigned(std::min<int64_t>(insts, sm_count));
@@ -206,12 +207,11 @@ static int march_width(int64_t outer, int64_t inner_bytes, int sm_count) {
     return (outer * ((inner_bytes + 127) / 128) * 2 >= sm_count) ? 128 : 0;
 }
 
-template <class In, class Acc, class Out> struct march_eligible { static constexpr bool value = false; };
-template <> struct march_eligible<float, float, float> { static constexpr bool value = true; };
-template <> struct march_eligible<double, double, double> { static constexpr bool value = true; };
-template <> struct march_eligible<int32_t, int32_t, int32_t> { static constexpr bool value = true; };
-template <> struct march_eligible<long long, long long, long long> { static constexpr bool value = true; };
-template <> struct march_eligible<unsigned long long, unsigned long long, unsigned long long> { static constexpr bool value = true; };
+// every pair of the scan table whose wider side has >= 2 bytes (a 512-byte strip of 1-byte items would exceed the
+// 256-element TMA box)
+template <class In, class Acc, class Out> struct march_eligible {
+    static constexpr bool value = (sizeof(In) > sizeof(Out) ? sizeof(In) : sizeof(Out)) >= 2;
+};
 
 // segments to cut n into so that outer * S * inner / V threads fill the GPU (1 = no split)
 static int64_t axis_split(int64_t outer, int64_t n, int64_t inner, int sm_count) {
@@ -267,13 +267,15 @@ static int run_axis(const void* xv, void* yv, int64_t outer, int64_t n, int64_t 
         Acc* tot = static_cast<Acc*>(ws);
         if constexpr (march_eligible<In, Acc, Out>::value) {
             static const bool force_split = getenv("B200_SCAN_AXIS_SPLIT") != nullptr;      // A/B knob: the two-read scheme
-            const int64_t inner_bytes = inner * int64_t(sizeof(In));
-            const int wb = (S > 1 && !force_split && inner_bytes % 16 == 0 && xa % 16 == 0 && ya % 16 == 0 &&
+            constexpr int SW = int(sizeof(In) > sizeof(Out) ? sizeof(In) : sizeof(Out));
+            const int64_t inner_bytes = inner * int64_t(SW);        // strip widths are counted on the wider side
+            const int wb = (S > 1 && !force_split && (inner * int64_t(sizeof(In))) % 16 == 0 &&
+                            (inner * int64_t(sizeof(Out))) % 16 == 0 && xa % 16 == 0 && ya % 16 == 0 &&
                             inner < (int64_t(1) << 31) && n < (int64_t(1) << 31) && outer < (int64_t(1) << 31))
                                ? march_width(outer, inner_bytes, sm_count) : 0;
-            if (wb == 512) return launch_march<In, Op, 512>(x, y, outer, n, inner, sm_count, s);
-            if (wb == 256) return launch_march<In, Op, 256>(x, y, outer, n, inner, sm_count, s);
-            if (wb == 128) return launch_march<In, Op, 128>(x, y, outer, n, inner, sm_count, s);
+            if (wb == 512) return launch_march<In, Acc, Out, Op, 512>(x, y, outer, n, inner, sm_count, s);
+            if (wb == 256) return launch_march<In, Acc, Out, Op, 256>(x, y, outer, n, inner, sm_count, s);
+            if (wb == 128) return launch_march<In, Acc, Out, Op, 128>(x, y, outer, n, inner, sm_count, s);
         }
         if (S > 1) {
             if (ws_bytes < size_t(outer * S * inner) * sizeof(Acc) || !ws)

@@ -126,18 +126,23 @@ def test_large_axis_scans(cp):
 MARCH_SHAPES = [(700, 16384), (1030, 4096), (300, 9000), (513, 2052), (3, 600, 4100), (2, 2049, 1540), (260, 40000)]
 
 
-@pytest.mark.parametrize('dt', ['int64', 'int32', 'uint64', 'float32', 'float64'])
+@pytest.mark.parametrize('dt', ['int64', 'int32', 'uint64', 'float32', 'float64', 'bool', 'int16', 'uint8', 'float16'])
 @pytest.mark.parametrize('shape', MARCH_SHAPES)
 def test_column_march_scans(cp, shape, dt):
     a = rnd(shape, dt)
+    if dt == 'float16':
+        a = (a / 64).astype(dt)
     d = cp.asarray(a)
     ax = len(shape) - 2
     got = d.cumsum(axis=ax).get()
     if np.dtype(dt).kind == 'f':
         want = a.astype(np.float64).cumsum(axis=ax)
-        np.testing.assert_allclose(got, want, rtol=0, atol=1e-3 if dt == 'float32' else 1e-10)
+        np.testing.assert_allclose(got, want, rtol=0, atol={'float32': 1e-3, 'float64': 1e-10, 'float16': 2e-2}[dt])
+        assert got.dtype == np.dtype(dt)
     else:
-        np.testing.assert_array_equal(got, a.cumsum(axis=ax))
+        want = a.cumsum(axis=ax)
+        assert got.dtype == want.dtype
+        np.testing.assert_array_equal(got, want)
     # cumprod: rows / columns past the edge of a tile must count as ones, not as the zeros TMA fills in
     p = np.where(RS.rand(*shape) < 0.002, 2, 1).astype(dt)
     got = cp.asarray(p).cumprod(axis=ax).get()
@@ -146,7 +151,8 @@ def test_column_march_scans(cp, shape, dt):
         np.testing.assert_allclose(got, want, rtol=1e-6)
     else:
         np.testing.assert_array_equal(got, want)
-    # in place (out= the input itself)
-    d2 = cp.asarray(a)
-    cp.cumsum(d2, axis=ax, out=d2)
-    np.testing.assert_array_equal(d2.get(), got if False else d.cumsum(axis=ax).get())
+    # in place (out= the input itself), where the result dtype is the input's
+    if got.dtype == a.dtype:
+        d2 = cp.asarray(a)
+        cp.cumsum(d2, axis=ax, out=d2)
+        np.testing.assert_array_equal(d2.get(), got)
