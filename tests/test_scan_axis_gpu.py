@@ -145,12 +145,12 @@ def test_column_march_scans(cp, shape, dt):
         np.testing.assert_array_equal(got, want)
     # cumprod: rows / columns past the edge of a tile must count as ones, not as the zeros TMA fills in
     p = np.where(RS.rand(*shape) < 0.002, 2, 1).astype(dt)
-    got = cp.asarray(p).cumprod(axis=ax).get()
-    want = p.cumprod(axis=ax)
+    gotp = cp.asarray(p).cumprod(axis=ax).get()
+    wantp = p.cumprod(axis=ax)
     if np.dtype(dt).kind == 'f':
-        np.testing.assert_allclose(got, want, rtol=1e-6)
+        np.testing.assert_allclose(gotp, wantp.astype(np.float64), rtol=1e-6 if dt != 'float16' else 1e-3)
     else:
-        np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(gotp, wantp)
     # in place (out= the input itself), where the result dtype is the input's
     if got.dtype == a.dtype:
         d2 = cp.asarray(a)
