@@ -311,10 +311,11 @@ def run_ours(args):
     assert abs(float(hz[N_ELEMS - 1]) - float(np.float32(1.5) * np.float32(0.25) + np.float32(0.5))) < 1e-6
 
     peak, peak_src = measured_peak()
-    traffic = None
+    traffic = traffic_src = None          # DRAM bytes of one axpy launch from the committed ncu --set full capture
     try:
         with open(os.path.join(ROOT, 'profiles', 'axpy_traffic.json')) as f:
-            traffic = json.load(f).get('dram_bytes_per_launch')
+            tj = json.load(f)
+        traffic, traffic_src = tj.get('dram_bytes_per_launch'), tj.get('source')
     except Exception:
         pass
 
@@ -339,6 +340,7 @@ def run_ours(args):
             'roofline': {'bound': 'hbm', 'kernel': 'axpy (FlatTiler<4,4,4,256> + user op via NVRTC)',
                          'achieved': round(BYTES_AXPY / (axpy_ms * 1e-3) / 1e9, 2), 'peak': peak, 'unit': 'GB/s',
                          'frac': round(BYTES_AXPY / (axpy_ms * 1e-3) / 1e9 / peak, 4), 'traffic': traffic,
+                         'traffic_source': traffic_src,
                          'peak_source': peak_src, 'avg_launch_ms': round(axpy_ms, 5),
                          'algorithmic_bytes_per_launch': BYTES_AXPY},
             'roofline_sum': {'bound': 'hbm', 'kernel': 'reduce_full_kernel<SumOp<float>,4,4>',
