@@ -62,6 +62,13 @@ def _stream_ctx(stream):
     return torch.cuda.stream(torch.cuda.ExternalStream(int(getattr(stream, 'ptr', stream))))
 
 
+def _cai_stream():
+    if _dryrun.enabled or not torch.cuda.is_available():
+        return 1
+    p = torch.cuda.current_stream().cuda_stream
+    return p if p else 1
+
+
 def current_stream_ptr():
     if _dryrun.enabled:
         return 0
@@ -267,7 +274,9 @@ class ndarray:
             'descr': self.dtype.descr,
             'data': (self.ptr, False),
             'version': 3,
-            'stream': 1,
+            # consumers must order their work after what is enqueued on the producing stream: torch's current one
+            # (1 = the legacy default stream, CUDA Array Interface v3)
+            'stream': _cai_stream(),
         }
         if not self._c_contiguous:
             desc['strides'] = self._strides
@@ -464,6 +473,9 @@ class ndarray:
         if self._mem is not None and isinstance(self._mem, torch.Tensor):
             off = self.ptr - self._mem.data_ptr()
             return self._mem[off:off + nbytes]
+        if isinstance(self._mem, _Keep):
+            # foreign device memory (imported through __cuda_array_interface__): hand torch a byte view of it
+            return torch.as_tensor(_ByteSpan(self.ptr, nbytes, self._mem), device='cuda')
         raise ValueError('array does not own torch-visible memory')
 
     def get(self, stream=None, order='C', out=None, blocking=True):
@@ -769,7 +781,8 @@ def asarray(a, dtype=None, order=None):
     if isinstance(a, torch.Tensor):
         return from_torch(a) if dtype is None else from_torch(a).astype(dtype)
     if hasattr(a, '__cuda_array_interface__'):
-        return from_cuda_array_interface(a)
+        r = from_cuda_array_interface(a)
+        return r if dtype is None or _scalar.get_dtype(dtype) == r.dtype else r.astype(dtype)
     h = numpy.asarray(a, dtype=dtype)
     # order 'K' (default): keep the memory order of the host array -- upload the bytes of the
     # axis permutation that is C-contiguous and view them with the permuted strides
@@ -826,6 +839,15 @@ def from_cuda_array_interface(obj):
 class _Keep:
     def __init__(self, obj):
         self.obj = obj
+
+
+class _ByteSpan:
+    """`nbytes` of foreign device memory as a CUDA-array-interface object (keeps the owner alive)."""
+
+    def __init__(self, ptr, nbytes, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {'shape': (int(nbytes),), 'typestr': '|u1', 'data': (int(ptr), False),
+                                         'version': 3, 'strides': None}
 
 
 def arange(start, stop=None, step=1, dtype=None):

@@ -752,3 +752,29 @@ def test_memoised_call_shapes_give_the_same_results_as_first_calls(cp):
         with pytest.raises(OverflowError):
             ui + 300                                          # NEP 50: Python int out of range for uint8, every time
         np.testing.assert_array_equal((ui + 5).get(), ui.get() + np.uint8(5))
+
+
+def test_cuda_array_interface_import_export(cp):
+    """arrays imported through __cuda_array_interface__ honour dtype=, can be read back
+    (.get / item / repr), and the exported dict names the producing stream."""
+    import torch
+    t = torch.arange(24, device='cuda', dtype=torch.float32).reshape(4, 6)
+
+    class Foreign:                      # a third-party CAI producer (not a torch.Tensor for asarray's eyes)
+        def __init__(self, t):
+            self.t = t
+            self.__cuda_array_interface__ = t.__cuda_array_interface__
+
+    a = cp.asarray(Foreign(t))
+    np.testing.assert_array_equal(a.get(), t.cpu().numpy())
+    assert float(a[1, 2].item()) == 8.0 and len(repr(a)) > 0
+    b = cp.asarray(Foreign(t), dtype=np.float64)
+    assert b.dtype == np.float64
+    np.testing.assert_array_equal(b.get(), t.cpu().numpy().astype(np.float64))
+    np.testing.assert_array_equal((a * 2).get(), t.cpu().numpy() * 2)
+    cai = a.__cuda_array_interface__
+    assert cai['stream'] == 1            # torch's current stream is the legacy default stream here
+    with cp.cuda.Stream(non_blocking=True) as s:
+        assert cp.empty((2,), 'f').__cuda_array_interface__['stream'] == s.ptr
+    back = torch.as_tensor(a * 1, device='cuda')
+    assert bool((back == t).all())
