@@ -112,6 +112,53 @@ def test_config4b_cumsum_int64_2p28(cp):
     del y, t
 
 
+def test_casting_scans_2p28(cp):
+    """the casting flat scans at full size, one read of x, bit-exact for integers.
+    Size-independent properties: differences recover the input, the last element is the total; the ragged end
+    (n not a multiple of the 128-item row granule) goes through the tail path."""
+    n = (1 << 28) + 77
+    g = torch.Generator(device='cuda').manual_seed(12)
+    t32 = torch.randint(-1000, 1000, (n,), device='cuda', generator=g, dtype=torch.int32)
+    y = cp.cumsum(cp.from_torch(t32)).to_torch()
+    assert y.dtype == torch.int64
+    assert bool((y[1:] - y[:-1] == t32[1:]).all().item()) and int(y[0]) == int(t32[0])
+    assert int(y[-1]) == int(t32.sum(dtype=torch.int64))
+    np.testing.assert_array_equal(y[-100000:].cpu().numpy() - int(y[-100001]),
+                                  oracle.cumsum(t32[-100000:].cpu().numpy().astype(np.int64)))
+    del y, t32
+    tb = torch.rand(n, device='cuda', generator=g) < 0.3
+    y = cp.cumsum(cp.from_torch(tb)).to_torch()
+    assert y.dtype == torch.int64
+    assert bool((y[1:] - y[:-1] == tb[1:].to(torch.int64)).all().item()) and int(y[-1]) == int(tb.sum())
+    del y, tb
+    # float16 with a float accumulator: one rounding per output (half an fp16 ulp) + the fp32 accumulation error
+    th = ((torch.rand(n, device='cuda', generator=g) * 2 - 1) / 64).half()
+    y = cp.cumsum(cp.from_torch(th)).to_torch()
+    assert y.dtype == torch.float16
+    ref = torch.cumsum(th.double(), 0)
+    ulp = torch.from_numpy(np.spacing(np.abs(ref.cpu().numpy()).astype(np.float16)).astype(np.float64)).cuda()
+    bound = 0.5 * ulp + 1e-6 * torch.cumsum(th.double().abs(), 0)
+    assert bool(((y.double() - ref).abs() <= bound).all().item())
+    del y, th, ref, ulp, bound
+
+
+def test_cumsum_axis0_16384_squared(cp):
+    """Column-march scan at the size DESIGN.md quotes: float32 within tolerance, int64 bit-exact."""
+    m = 16384
+    t = gen((m, m), torch.float32, 13)
+    y = cp.cumsum(cp.from_torch(t), axis=0).to_torch()
+    ref_last = t.double().sum(dim=0)
+    assert float((y[-1].double() - ref_last).abs().max()) <= 1e-5 * float(t.double().abs().sum(dim=0).max())
+    assert bool(torch.allclose(y[1:] - y[:-1], t[1:], atol=2e-3))           # differences recover the input
+    np.testing.assert_allclose(y[:, :64].cpu().numpy(), np.cumsum(t[:, :64].cpu().numpy().astype(np.float64), axis=0),
+                               atol=2e-3)
+    del y
+    ti = torch.randint(-1000, 1000, (m // 2, m), device='cuda', dtype=torch.int64)
+    yi = cp.cumsum(cp.from_torch(ti), axis=0).to_torch()
+    assert bool(torch.equal(yi, torch.cumsum(ti, 0)))
+    del t, ti, yi
+
+
 def test_full_reductions_2p28_and_beyond_int32_indexing(cp):
     n = 1 << 28
     t = gen((n,), torch.float32, 21)
