@@ -18,6 +18,8 @@ from cupy_b200._core._routines_math import (  # noqa: F401
     expm1, exp2, log2, log10, log1p, sin, cos, tan, tanh, sinh, cosh, arctan2, hypot,
     maximum, minimum, power, fma, greater, greater_equal, less, less_equal, equal, not_equal,
     sum, prod, cumsum, cumprod)
+from cupy_b200._core._routines_binary import (  # noqa: F401
+    bitwise_and, bitwise_or, bitwise_xor, bitwise_not, invert, left_shift, right_shift)
 from cupy_b200._core._routines_statistics import (  # noqa: F401
     amax, amin, argmax, argmin, mean, var, std)
 

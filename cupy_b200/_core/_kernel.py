@@ -877,8 +877,9 @@ class ufunc:
     """Universal function (drop-in for cupy.ufunc, cupy/_core/_kernel.pyx:1147-1493)."""
 
     def __init__(self, name, nin, nout, ops, preamble='', loop_prep='', doc='',
-                 default_casting=None, out_ops=None, prebuilt=None):
+                 default_casting=None, out_ops=None, prebuilt=None, scatter_op=None):
         self.name = name
+        self._scatter_op = scatter_op
         self.__name__ = name
         self.nin = nin
         self.nout = nout
@@ -1123,7 +1124,11 @@ class ufunc:
         return self(A, B, **kwargs)
 
     def at(self, a, indices, b=None):
-        raise NotImplementedError('`%s.at` is not supported yet' % self.name)
+        """In-place `a[indices] = ufunc(a[indices], b)` with repeated indices accumulated (_kernel.pyx:1446-1457)."""
+        if self._scatter_op is None:
+            raise NotImplementedError('`%s.at` is not supported yet' % self.name)
+        from cupy_b200._core import _scatter
+        _scatter.scatter_op(a, indices, b, self._scatter_op)
 
     def reduce(self, array, axis=0, dtype=None, out=None, keepdims=False):
         if self.name == 'cupy_add':
@@ -1142,15 +1147,18 @@ class ufunc:
         raise NotImplementedError('`%s.accumulate` is not supported yet' % self.name)
 
     def reduceat(self, array, indices, axis=0, dtype=None, out=None):
+        if self.name == 'cupy_add':
+            from cupy_b200._core import _scatter
+            return _scatter.add_reduceat(array, indices, axis, dtype, out)
         raise NotImplementedError('`%s.reduceat` is not supported yet' % self.name)
 
 
 def create_ufunc(name, ops, routine=None, preamble='', doc='', default_casting=None,
-                 loop_prep='', out_ops=None, prebuilt=None):
+                 loop_prep='', out_ops=None, prebuilt=None, scatter_op=None):
     ops_ = _Ops.from_tuples(ops, routine)
     _out_ops = None if out_ops is None else _Ops.from_tuples(out_ops, routine)
     return ufunc(name, ops_.nin, ops_.nout, ops_, preamble, loop_prep, doc,
-                 default_casting=default_casting, out_ops=_out_ops, prebuilt=prebuilt)
+                 default_casting=default_casting, out_ops=_out_ops, prebuilt=prebuilt, scatter_op=scatter_op)
 
 
 # ---------------------------------------------------------------------------

@@ -622,8 +622,8 @@ class ndarray:
     def _binop(self, name, other, reflected=False):
         f = _UFUNCS.get(name)
         if f is None:
-            from cupy_b200._core import _routines_math as m
-            f = _UFUNCS[name] = getattr(m, name)
+            from cupy_b200._core import _routines_math as m, _routines_binary as b
+            f = _UFUNCS[name] = getattr(m, name, None) or getattr(b, name)
         to = type(other)
         if (to is ndarray or to is float or to is int or to is bool
                 or isinstance(other, (ndarray, int, float, bool, numpy.generic))
@@ -641,14 +641,32 @@ class ndarray:
     def __rtruediv__(self, o): return self._binop('true_divide', o, True)
 
     def _ibinop(self, name, other):
-        from cupy_b200._core import _routines_math as m
-        getattr(m, name)(self, other, out=self)
+        from cupy_b200._core import _routines_math as m, _routines_binary as b
+        (getattr(m, name, None) or getattr(b, name))(self, other, out=self)
         return self
 
     def __iadd__(self, o): return self._ibinop('add', o)
     def __isub__(self, o): return self._ibinop('subtract', o)
     def __imul__(self, o): return self._ibinop('multiply', o)
     def __itruediv__(self, o): return self._ibinop('true_divide', o)
+
+    def __and__(self, o): return self._binop('bitwise_and', o)
+    def __rand__(self, o): return self._binop('bitwise_and', o, True)
+    def __or__(self, o): return self._binop('bitwise_or', o)
+    def __ror__(self, o): return self._binop('bitwise_or', o, True)
+    def __xor__(self, o): return self._binop('bitwise_xor', o)
+    def __rxor__(self, o): return self._binop('bitwise_xor', o, True)
+    def __lshift__(self, o): return self._binop('left_shift', o)
+    def __rlshift__(self, o): return self._binop('left_shift', o, True)
+    def __rshift__(self, o): return self._binop('right_shift', o)
+    def __rrshift__(self, o): return self._binop('right_shift', o, True)
+    def __iand__(self, o): return self._ibinop('bitwise_and', o)
+    def __ior__(self, o): return self._ibinop('bitwise_or', o)
+    def __ixor__(self, o): return self._ibinop('bitwise_xor', o)
+
+    def __invert__(self):
+        from cupy_b200._core import _routines_binary as b
+        return b.invert(self)
 
     def __lt__(self, o): return self._binop('less', o)
     def __le__(self, o): return self._binop('less_equal', o)

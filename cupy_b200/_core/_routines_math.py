@@ -21,13 +21,13 @@ _INT_LOOPS = ('bb->b', 'BB->B', 'hh->h', 'HH->H', 'ii->i', 'II->I', 'll->l', 'LL
 _INT_LOOPS1 = ('b->b', 'B->B', 'h->h', 'H->H', 'i->i', 'I->I', 'l->l', 'L->L', 'q->q', 'Q->Q')
 
 
-def _create_arithmetic(name, op, boolop, doc=''):
+def _create_arithmetic(name, op, boolop, doc='', scatter_op=None):
     if isinstance(boolop, str):
         boolop = 'out0 = in0 %s in1' % boolop
     return create_ufunc(
         'cupy_' + name,
         (('??->?', boolop),) + _INT_LOOPS + ('ee->e', 'ff->f', 'dd->d'),
-        'out0 = in0 %s in1' % op, doc=doc, prebuilt=name)
+        'out0 = in0 %s in1' % op, doc=doc, prebuilt=name, scatter_op=scatter_op)
 
 
 def _subtract_boolean_error():
@@ -40,8 +40,9 @@ def _negative_boolean_error():
                     'use the `~` operator or the logical_not function instead.')
 
 
-add = _create_arithmetic('add', '+', '|', 'Adds two arrays elementwise.')
-subtract = _create_arithmetic('subtract', '-', _subtract_boolean_error, 'Subtracts arguments elementwise.')
+add = _create_arithmetic('add', '+', '|', 'Adds two arrays elementwise.', scatter_op='add')
+subtract = _create_arithmetic('subtract', '-', _subtract_boolean_error, 'Subtracts arguments elementwise.',
+                              scatter_op='sub')
 multiply = _create_arithmetic('multiply', '*', '&', 'Multiplies two arrays elementwise.')
 
 true_divide = create_ufunc(
@@ -105,12 +106,14 @@ maximum = create_ufunc(
     'cupy_maximum',
     ('??->?',) + _INT_LOOPS + (('ee->e', _float_maximum), ('ff->f', _float_maximum), ('dd->d', _float_maximum)),
     'out0 = max(in0, in1)', preamble=_float_preamble,
-    doc='Takes the maximum of two arrays elementwise. If NaN appears, it returns the NaN.', prebuilt='maximum')
+    doc='Takes the maximum of two arrays elementwise. If NaN appears, it returns the NaN.', prebuilt='maximum',
+    scatter_op='max')
 minimum = create_ufunc(
     'cupy_minimum',
     ('??->?',) + _INT_LOOPS + (('ee->e', _float_minimum), ('ff->f', _float_minimum), ('dd->d', _float_minimum)),
     'out0 = min(in0, in1)', preamble=_float_preamble,
-    doc='Takes the minimum of two arrays elementwise. If NaN appears, it returns the NaN.', prebuilt='minimum')
+    doc='Takes the minimum of two arrays elementwise. If NaN appears, it returns the NaN.', prebuilt='minimum',
+    scatter_op='min')
 
 power = create_ufunc(
     'cupy_power',

@@ -549,3 +549,28 @@ def test_call_shape_memo_of_the_launcher(dry):
     a2 = cp.empty((64, 48), 'f')
     out = a2.sum(axis=0)
     assert dry[-1] == rec and out.shape == (48,)
+
+
+def test_ufunc_at_and_reduceat_kernels_compile_for_every_supported_dtype(dry):
+    """ufunc.at / add.reduceat (cupy_b200/_core/_scatter.py): every dtype gate of the reference's
+    _scatter_op_single (_routines_indexing.pyx:942-1018) has an atomic overload that NVRTC accepts."""
+    import cupy_b200 as cp
+    from cupy_b200._core import _scatter
+    for op, dts in _scatter._SUPPORTED.items():
+        for dt in dts:
+            getattr(cp, _scatter._UFUNC_NAME[op]).at(cp.empty((100,), dt), cp.empty((30,), 'int64'), cp.empty((30,), dt))
+    cp.add.at(cp.empty((10, 20, 3), 'int64'), (cp.empty((4, 1), 'int32'), cp.empty((1, 5), 'int64')),
+              cp.empty((4, 5, 3), 'int64'))
+    n_at = len(dry)
+    assert n_at >= sum(len(v) for v in _scatter._SUPPORTED.values())
+    r = cp.add.reduceat(cp.empty((37, 50), 'int32'), [0, 3, 5], axis=1)
+    assert r.shape == (37, 3) and r.dtype == np.int64
+    assert [d['kind'] for d in dry[n_at:]] == ['prebuilt_scan_axis', 'jit_elementwise']
+    with pytest.raises(TypeError):
+        cp.add.at(cp.empty((4,), 'int8'), cp.empty((1,), 'int64'), 1)
+    with pytest.raises(NotImplementedError):
+        cp.multiply.at(cp.empty((4,), 'float32'), cp.empty((1,), 'int64'), 1.0)
+    with pytest.raises(NotImplementedError):
+        cp.add.at(cp.empty((4, 4), 'float32'), (slice(None), cp.empty((1,), 'int64')), 1.0)
+    with pytest.raises(IndexError):
+        cp.add.reduceat(cp.empty((10,), 'int32'), [0, 10])
