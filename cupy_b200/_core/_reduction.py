@@ -181,16 +181,19 @@ class _AbstractReductionKernel:
         # ---- memoised call shape of the prebuilt route (one dense input, fresh output): everything below depends
         # only on (dtype, shape, strides, alignment, axis, dtype=, keepdims, param)
         mkey = None
-        if (len(in_args) == 1 and not out_args and stream is None and type(in_args[0]) is ndarray
+        given = out_args[0] if out_args else None
+        if (len(in_args) == 1 and stream is None and type(in_args[0]) is ndarray
+                and (given is None or (len(out_args) == 1 and type(given) is ndarray and given._c_contiguous))
                 and self._prebuilt_op is not None and _accelerator.fast_paths_enabled()):
             a = in_args[0]
             ax = tuple(axis) if isinstance(axis, list) else axis
-            mkey = (a.dtype, a._shape, a._strides, a.ptr & 15, ax, dtype, bool(keepdims), float(param))
+            mkey = (a.dtype, a._shape, a._strides, a.ptr & 15, ax, dtype, bool(keepdims), float(param),
+                    None if given is None else (given.dtype, given._shape, given.ptr & 15))
             memo = _kernel._thread_local.__dict__.setdefault('reduce_memo', {}).setdefault(id(self), {})
             e = memo.get(mkey)
             if e is not None and not (_dryrun.enabled and e[6] is None):
                 desc, oshape, odtype, ostrides, osize, need, dry = e
-                out = ndarray._fresh(oshape, odtype, ostrides, osize)
+                out = ndarray._fresh(oshape, odtype, ostrides, osize) if given is None else given
                 if _dryrun.enabled:
                     _dryrun.log.append(dict(dry))
                     return out

@@ -12,7 +12,7 @@ import ctypes
 import numpy
 
 from cupy_b200 import _lib
-from cupy_b200._core import _kernel, _scalar, _workspace
+from cupy_b200._core import _accelerator, _dryrun, _kernel, _scalar, _workspace
 from cupy_b200._core._kernel import create_ufunc
 from cupy_b200._core._ndarray import ndarray, normalize_axis_index, current_stream_ptr
 from cupy_b200._core._reduction import create_reduction_func
@@ -233,7 +233,6 @@ def _scan_flat(src, dst, op):
             _kernel.elementwise_copy(tmp_out, dst)
             return
         return _scan_flat(tmp_in, dst, op)
-    from cupy_b200._core import _dryrun
     if _dryrun.enabled:
         _dryrun.record('prebuilt_scan', op=op, n=n, in_dtype=src.dtype.name, out_dtype=dst.dtype.name)
         return
@@ -246,12 +245,34 @@ def _scan_flat(src, dst, op):
 def scan_core(a, axis, op, dtype=None, out=None):
     """cupy/_core/_routines_math.pyx:702-751 (dtype rules :704-714)."""
     a = _as_array(a)
-    from cupy_b200._core import _accelerator
     if _accelerator.reference_first(routine=True):
         r = _accelerator.try_reference('scan', 'cumsum' if op == _lib.OP_CUMSUM else 'cumprod', a,
                                        axis=axis, dtype=dtype, out=out)
         if r is not None:
             return r
+    # ---- memoised call shape (dense input, fresh output, prebuilt pair): what the rest of this function derives
+    # depends only on (dtype, shape, strides, alignment, axis, dtype=, op)
+    mkey = None
+    if out is None and type(a) is ndarray and a._c_contiguous and a.size and _accelerator.fast_paths_enabled():
+        mkey = (a.dtype, a._shape, a.ptr & 15, axis, dtype, op, _kernel._memo_epoch)
+        memo = _kernel._thread_local.__dict__.setdefault('scan_memo', {})
+        e = memo.get(mkey)
+        if e is not None and not _dryrun.enabled:
+            in_id, out_id, oshape, odtype, ostrides, geom, need = e
+            res = ndarray._fresh(oshape, odtype, ostrides, a.size)
+            st = current_stream_ptr()
+            if geom is None:
+                ws_ptr, ws_bytes = _workspace.get(16384 + need, st)
+                _lib.check(_lib.lib.b200_scan_run(op, in_id, out_id, a.ptr, res.ptr, a.size, ws_ptr + 16384,
+                                                  ws_bytes - 16384, st))
+            else:
+                ws_ptr = 0
+                if need:
+                    scratch = ndarray._fresh((need,), _U8, (1,), need)
+                    ws_ptr = scratch.ptr
+                _lib.check(_lib.lib.b200_scan_axis_run(op, in_id, out_id, a.ptr, res.ptr, geom[0], geom[1], geom[2],
+                                                       ws_ptr, need, st))
+            return res
     if out is None:
         if dtype is None:
             kind = a.dtype.kind
@@ -277,12 +298,36 @@ def scan_core(a, axis, op, dtype=None, out=None):
             return out
         result = ndarray((a.size,), dtype)
         _scan_flat(src, result, op)
+        if mkey is not None and src.ptr % 16 == 0 and result.ptr % 16 == 0 and not _dryrun.enabled:
+            in_id, out_id = _scalar.dtype_id(src.dtype), _scalar.dtype_id(result.dtype)
+            if _lib.lib.b200_scan_supported(op, in_id, out_id):
+                need = ctypes.c_size_t()
+                _lib.check(_lib.lib.b200_scan_workspace_bytes(a.size, out_id, ctypes.byref(need)))
+                _remember_scan(mkey, (in_id, out_id, result._shape, result.dtype, result._strides, None, need.value))
         if out is not None:
             _kernel.elementwise_copy(result.reshape(out.shape), out)
             return out
         return result
     axis = normalize_axis_index(axis, a.ndim)
-    return _scan_axis(a, axis, op, dtype, out)
+    res = _scan_axis(a, axis, op, dtype, out)
+    if mkey is not None and not _dryrun.enabled:
+        in_id, out_id = _scalar.dtype_id(a.dtype), _scalar.dtype_id(dtype)
+        if _lib.lib.b200_scan_supported(op, in_id, out_id) and res._c_contiguous:
+            geom = (_kernel._prod(a.shape[:axis]), int(a.shape[axis]), _kernel._prod(a.shape[axis + 1:]))
+            need = ctypes.c_size_t()
+            _lib.check(_lib.lib.b200_scan_axis_workspace_bytes(geom[0], geom[1], geom[2], ctypes.byref(need)))
+            _remember_scan(mkey, (in_id, out_id, res._shape, res.dtype, res._strides, geom, need.value))
+    return res
+
+
+_U8 = numpy.dtype('uint8')
+
+
+def _remember_scan(mkey, entry):
+    memo = _kernel._thread_local.__dict__.setdefault('scan_memo', {})
+    if len(memo) >= 512:
+        memo.clear()
+    memo[mkey] = entry
 
 
 def _scan_axis(a, axis, op, dtype, out):

@@ -13,7 +13,7 @@ import math
 import numpy
 
 from cupy_b200 import _lib
-from cupy_b200._core import _kernel, _scalar
+from cupy_b200._core import _accelerator, _kernel, _scalar
 from cupy_b200._core import _routines_math as _math
 from cupy_b200._core._ndarray import ndarray
 from cupy_b200._core._reduction import ReductionKernel, create_reduction_func, _get_axis
@@ -214,10 +214,19 @@ class _VarKernel:
 
 
 _var_single_pass = _VarKernel()
+_var_hot = {}      # (dtype, shape, strides, axis) -> normalised axis tuple of call shapes the single pass takes
 
 
 def _var(a, axis=None, dtype=None, out=None, ddof=0, keepdims=False):
     """cupy/_core/_routines_statistics.pyx:556-600."""
+    hot_key = None
+    fast = _accelerator.fast_paths_enabled()     # the single-pass functor is one of the accelerated routes
+    if dtype is None and out is None and fast:
+        # call shapes already found eligible for the single-pass functor skip the layout analysis below
+        hot_key = (a.dtype, a._shape, a._strides, tuple(axis) if isinstance(axis, list) else axis)
+        hot_axis = _var_hot.get(hot_key)
+        if hot_axis is not None:
+            return _var_single_pass(a, hot_axis, ddof, keepdims)
     if axis is None:
         axis = tuple(range(a.ndim))
     if not isinstance(axis, tuple):
@@ -237,7 +246,7 @@ def _var(a, axis=None, dtype=None, out=None, ddof=0, keepdims=False):
         items *= a.shape[ax]
 
     # ---- hot path: one read of `a` (the reference reads it twice)
-    if dtype is None and out is None and a.size > 0 and items > 0:
+    if fast and dtype is None and out is None and a.size > 0 and items > 0:
         from cupy_b200._core import _reduction
         layout = _reduction._classify(a.shape, a.strides, a.dtype.itemsize, reduce_axis, out_axis, False)
         if layout.kind >= 0:
@@ -246,6 +255,9 @@ def _var(a, axis=None, dtype=None, out=None, ddof=0, keepdims=False):
                                    layout.n_out, float(ddof))
             import ctypes
             if _lib.lib.b200_reduce_supported(ctypes.byref(desc)):
+                if len(_var_hot) >= 512:
+                    _var_hot.clear()
+                _var_hot[hot_key] = axis
                 return _var_single_pass(a, axis, ddof, keepdims)
 
     # ---- general path: the reference's algorithm (mean, then sum of squared deviations)

@@ -490,6 +490,10 @@ def test_accelerator_switch_and_numpy_dispatch(dry):
     try:
         x.sum(axis=1)
         assert dry[-1]['kind'] == 'jit_reduce' and 'generic' in dry[-1]['name']
+        # var without the accelerated single pass is the reference's two passes (mean, then cupy_var_core)
+        del dry[:]
+        x.var(axis=1)
+        assert [d['kind'] for d in dry] == ['jit_reduce', 'jit_reduce'] and 'var_core' in dry[-1]['name']
         cp.set_reduction_accelerators(['reference'])
         with pytest.raises(RuntimeError):                  # nothing registered: the package has no oracle
             x.sum(axis=1)

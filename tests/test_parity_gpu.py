@@ -754,6 +754,85 @@ def test_memoised_call_shapes_give_the_same_results_as_first_calls(cp):
         np.testing.assert_array_equal((ui + 5).get(), ui.get() + np.uint8(5))
 
 
+def test_memoised_scans_reductions_with_out_and_generic_accelerator(cp):
+    """Memoised call shapes of the scans (flat and axis), of reductions into a given `out=`, and of var; and the
+    same calls with the accelerated routes switched off (CUPY_ACCELERATORS-style 'generic'): var is then the
+    reference's two passes, never the single-pass functor's stand-in routine."""
+    rs = np.random.RandomState(34)
+    for rep in range(3):
+        a = rs.randint(-50, 50, size=(130, 257)).astype(np.int32)
+        f = (rs.rand(130, 257) * 2 - 1).astype(np.float32)
+        da, df = cp.asarray(a), cp.asarray(f)
+        np.testing.assert_array_equal(cp.cumsum(da).get(), np.cumsum(a))
+        np.testing.assert_array_equal(cp.cumsum(da, axis=0).get(), np.cumsum(a, axis=0))
+        np.testing.assert_array_equal(cp.cumsum(da, axis=1).get(), np.cumsum(a, axis=1))
+        np.testing.assert_array_equal(cp.cumprod(da[:, :3], axis=1).get(), np.cumprod(a[:, :3], axis=1))   # not dense
+        np.testing.assert_array_equal(cp.cumsum(da, dtype='int32').get(), np.cumsum(a, dtype='int32'))
+        big = cp.asarray(np.arange(1 << 21, dtype=np.int64) % (7 + rep))
+        np.testing.assert_array_equal(cp.cumsum(big).get(), np.cumsum(big.get()))
+        o = cp.empty((130,), np.int64)
+        assert da.sum(axis=1, out=o) is o
+        np.testing.assert_array_equal(o.get(), a.sum(axis=1))
+        o2 = cp.empty((257,), np.float32)
+        df.max(axis=0, out=o2)
+        np.testing.assert_array_equal(o2.get(), f.max(axis=0))
+        with pytest.raises(ValueError):
+            da.sum(axis=1, out=cp.empty((131,), np.int64))
+        for ddof in (0, 1):
+            np.testing.assert_allclose(df.var(axis=1, ddof=ddof).get(), f.astype(np.float64).var(axis=1, ddof=ddof), rtol=1e-4)
+            np.testing.assert_allclose(df.var(ddof=ddof).get(), f.astype(np.float64).var(ddof=ddof), rtol=1e-4)
+    cp.set_reduction_accelerators(['generic'])
+    try:
+        np.testing.assert_allclose(df.var(axis=1).get(), f.astype(np.float64).var(axis=1), rtol=1e-4)
+        np.testing.assert_allclose(df.var(axis=0, ddof=1).get(), f.astype(np.float64).var(axis=0, ddof=1), rtol=1e-4)
+        np.testing.assert_allclose(df.std().get(), f.astype(np.float64).std(), rtol=1e-4)
+        np.testing.assert_array_equal(da.sum(axis=1).get(), a.sum(axis=1))
+        np.testing.assert_array_equal(df.argmax(axis=0).get(), f.argmax(axis=0))
+    finally:
+        cp.set_reduction_accelerators(['b200'])
+    np.testing.assert_allclose(df.var(axis=1).get(), f.astype(np.float64).var(axis=1), rtol=1e-4)
+
+
+def test_cuda_graph_capture_and_replay(cp):
+    """Launches go to the current stream with no host synchronisation, so a sequence of them -- NVRTC elementwise,
+    fused, row reduction, ticketed full reduction, cooperative pipelined scan -- can be captured in a CUDA graph
+    and replayed on new data in the same buffers (kernel memo, workspace and outputs are created by the warm-up)."""
+    import torch
+    n = 1 << 21
+    tx = torch.rand(1024, 2048, device='cuda') * 2 - 1
+    ti = torch.randint(-100, 100, (n,), device='cuda', dtype=torch.int64)
+    x, xi = cp.from_torch(tx), cp.from_torch(ti)
+    fz = cp.fuse(kernel_name='graph_x2p1')(lambda a: a * 2 + 1)
+
+    def step():
+        y = fz(x)
+        return y, y.sum(axis=1), x.sum(), x.argmax(axis=0), cp.cumsum(xi), cp.cumsum(x, axis=0)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        outs = step()
+    for seed in (1, 2):
+        gen = torch.Generator(device='cuda').manual_seed(seed)
+        tx.copy_(torch.rand(1024, 2048, device='cuda', generator=gen) * 2 - 1)
+        ti.copy_(torch.randint(-100, 100, (n,), device='cuda', dtype=torch.int64, generator=gen))
+        g.replay()
+        torch.cuda.synchronize()
+        y, rows, total, arg, scan, scan0 = [o.to_torch() for o in outs]
+        assert bool(torch.equal(y, tx * 2 + 1))
+        assert bool(torch.allclose(rows.double(), (tx * 2 + 1).double().sum(1), atol=1e-3))
+        assert abs(float(total) - float(tx.double().sum())) < 1e-2
+        assert bool(torch.equal(arg, tx.argmax(0)))
+        assert bool(torch.equal(scan, torch.cumsum(ti, 0)))
+        assert bool(torch.allclose(scan0.double(), torch.cumsum(tx.double(), 0), atol=1e-3))
+
+
 def test_cuda_array_interface_import_export(cp):
     """arrays imported through __cuda_array_interface__ honour dtype=, can be read back
     (.get / item / repr), and the exported dict names the producing stream."""
