@@ -32,6 +32,47 @@ def _median_ms(f, iters=10, warm=3):
     return float(ts[len(ts) // 2]), float(ts[0])
 
 
+def _graph_us(f, inner=20, replays=10):
+    """Per-launch time of `f` inside a replayed CUDA graph: the kernel (plus launch gaps) with the per-call host cost
+    taken out -- for the L2-resident / tiny configs whose per-call time is the host's."""
+    import torch
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                f()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(inner):
+                f()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(replays):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / (inner * replays) * 1e3
+    except Exception:            # capture is evidence beside the bench line, never a reason to lose it
+        torch.cuda.synchronize()
+        return None
+
+
+def _with_graph(e, f, nbytes, peak):
+    us = _graph_us(f)
+    if us is not None:
+        e['graph_replay_us'] = round(us, 2)
+        if nbytes:
+            e['graph_replay_gbs'] = round(nbytes / us / 1e3, 1)
+            e['graph_replay_frac'] = round(nbytes / us / 1e3 / peak, 4)
+    return e
+
+
 def _entry(name, nbytes, ms, peak, check, **kw):
     gbs = nbytes / (ms * 1e-3) / 1e9
     e = {'name': name, 'ms': round(ms, 5), 'bytes': int(nbytes), 'gbs': round(gbs, 1), 'frac': round(gbs / peak, 4),
@@ -115,16 +156,19 @@ def run_configs(peak, with_ref_gpu=True, quick=False):
     fz = cp.fuse(kernel_name='c1_x2p1')(lambda a: a * 2 + 1)
     ms, _ = _median_ms(lambda: fz(x1), iters=50)
     ok = bool(torch.equal(fz(x1).to_torch(), t1 * 2 + 1))
-    entries.append(_entry('C1 x*2+1 f32 4096^2 (cupy_b200.fuse, one kernel)', 2 * 4 * 4096 * 4096, ms, peak,
-                          'bit-exact' if ok else 'MISMATCH', l2_resident=True))
+    entries.append(_with_graph(_entry('C1 x*2+1 f32 4096^2 (cupy_b200.fuse, one kernel)', 2 * 4 * 4096 * 4096, ms, peak,
+                                      'bit-exact' if ok else 'MISMATCH', l2_resident=True),
+                               lambda: fz(x1), 2 * 4 * 4096 * 4096, peak))
     ms, _ = _median_ms(lambda: x1 * 2 + 1, iters=50)
     entries.append(_entry('C1 x*2+1 f32 4096^2 (two ufunc launches; bytes = fused-equivalent)', 2 * 4 * 4096 * 4096, ms,
                           peak, 'bit-exact' if bool(torch.equal((x1 * 2 + 1).to_torch(), t1 * 2 + 1)) else 'MISMATCH',
                           l2_resident=True))
     ms, _ = _median_ms(lambda: x1.sum(axis=1), iters=50)
     err = float((x1.sum(axis=1).to_torch().double() - t1.double().sum(1)).abs().max())
-    entries.append(_entry('C1 x.sum(axis=1) f32 4096^2', 4 * 4096 * 4096 + 4 * 4096, ms, peak,
-                          'ok max_abs_err=%.2e' % err if err < 1e-3 else 'MISMATCH %.3e' % err, l2_resident=True))
+    entries.append(_with_graph(_entry('C1 x.sum(axis=1) f32 4096^2', 4 * 4096 * 4096 + 4 * 4096, ms, peak,
+                                      'ok max_abs_err=%.2e' % err if err < 1e-3 else 'MISMATCH %.3e' % err,
+                                      l2_resident=True),
+                               lambda: x1.sum(axis=1), 4 * 4096 * 4096 + 4 * 4096, peak))
     del x1, t1
 
     # ---------------- small-array floor (performance.rst:33-34: arange(1000).sum()) --------------
@@ -148,6 +192,7 @@ def run_configs(peak, with_ref_gpu=True, quick=False):
     add_us = (time.perf_counter() - t0) / 2000 * 1e6
     torch.cuda.synchronize()
     entries.append({'name': 'small-array floor: arange(1000).sum() / add(a,b) on 1000 f32',
+                    'graph_replay_us_sum': _graph_us(lambda: xs.sum()),
                     'host_us_per_call_sum': round(host_us, 2), 'host_us_per_call_add': round(add_us, 2),
                     'gpu_us_per_call_sum': round(gpu_ms * 1e3, 2),
                     'check': 'ok' if int(xs.sum().get()) == 499500 else 'MISMATCH',

@@ -15,8 +15,6 @@ from __future__ import annotations
 
 import re
 
-import numpy
-
 from cupy_b200 import _lib
 from cupy_b200._core._scalar import get_dtype, get_typename
 

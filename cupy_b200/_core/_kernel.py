@@ -22,7 +22,6 @@ from __future__ import annotations
 import ctypes
 import os as _os
 import re as _re
-import string
 import threading
 
 import numpy

@@ -69,9 +69,17 @@ def _cai_stream():
     return p if p else 1
 
 
+# torch's raw accessors: the cudaStream_t of the calling thread's current stream without building a
+# torch.cuda.Stream object around it (5 us on the GPU box's host, a third of a small call; profiles/r02_host_cost.log)
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+_raw_device = getattr(torch._C, '_cuda_getDevice', None)
+
+
 def current_stream_ptr():
     if _dryrun.enabled:
         return 0
+    if _raw_stream is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -21,11 +21,9 @@ from __future__ import annotations
 
 import ctypes
 
-import numpy
-
 from cupy_b200 import _lib
 from cupy_b200._core import _accelerator, _codegen_reduce, _dryrun, _jit, _kernel, _scalar, _workspace
-from cupy_b200._core._kernel import (ParameterInfo, _broadcast, _decide_params_type_core,
+from cupy_b200._core._kernel import (_broadcast, _decide_params_type_core,
                                      _get_param_info, _preprocess_args, _stream_ptr)
 from cupy_b200._core._ndarray import ndarray, normalize_axis_index, current_stream_ptr
 from cupy_b200._core._scalar import CScalar, get_dtype, get_typename

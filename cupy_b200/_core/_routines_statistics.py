@@ -13,7 +13,7 @@ import math
 import numpy
 
 from cupy_b200 import _lib
-from cupy_b200._core import _accelerator, _kernel, _scalar
+from cupy_b200._core import _accelerator, _scalar
 from cupy_b200._core import _routines_math as _math
 from cupy_b200._core._ndarray import ndarray
 from cupy_b200._core._reduction import ReductionKernel, create_reduction_func, _get_axis

@@ -1,4 +1,4 @@
-import sys, numpy as np, torch
+import sys, torch
 sys.path.insert(0, ".")
 import cupy_b200 as cp
 from bench_configs import _median_ms

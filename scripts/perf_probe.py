@@ -1,5 +1,5 @@
 """Device-timed GB/s of the configs in BASELINE.json (development probe; bench.py is the contract)."""
-import sys, json
+import sys
 import numpy as np
 sys.path.insert(0, '.')
 import torch

@@ -5,7 +5,6 @@ import ctypes
 import os
 import re
 
-import numpy as np
 import pytest
 
 from cupy_b200 import _lib

@@ -456,7 +456,6 @@ def test_moments_single_pass_mean_m2(cp, n, dt):
 
 def test_moments_merge_is_chan_in_rank_order(cp):
     """b200_moments_merge against NumPy on the concatenated shards, empty shards included."""
-    import ctypes
     from cupy_b200 import _lib
     from cupy_b200._core._kernel import current_stream_ptr
     from cupy_b200._core._routines_statistics import moments
