@@ -1,0 +1,205 @@
+"""GPU tier: seeded differential fuzz against NumPy over the whole hot path -- random shapes (0..4-d, with empty and
+unit extents), dtypes, views (steps, negative steps, transposes, broadcasts), axes, keepdims, `out=` -- the way the
+reference's `testing.numpy_cupy_*` decorators compare every routine (tests/cupy_tests/math_tests/test_sumprod.py,
+core_tests/test_ndarray_reduction.py, core_tests/test_ufunc_methods.py), but generated rather than enumerated.
+Integer / bool / index results are bit-exact; floating results within a bound scaled by the reduced magnitude."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = ['bool', 'int8', 'uint8', 'int16', 'int32', 'uint32', 'int64', 'uint64', 'float16', 'float32', 'float64']
+
+
+@pytest.fixture(scope='module')
+def cp():
+    import cupy_b200
+    return cupy_b200
+
+
+def _rand_shape(rs, max_ndim=4, big=False):
+    nd = rs.randint(0, max_ndim + 1)
+    choices = [0, 1, 2, 3, 5, 8, 17, 33, 64, 100, 257] + ([1024, 4099] if big else [])
+    shape = tuple(int(rs.choice(choices)) for _ in range(nd))
+    while np.prod(shape, dtype=np.int64) > (1 << 22):
+        shape = shape[:-1]
+    return shape
+
+
+def _rand_data(rs, shape, dt):
+    dt = np.dtype(dt)
+    if dt.kind == 'b':
+        return rs.rand(*shape) < 0.5
+    if dt.kind == 'f':
+        return ((rs.rand(*shape) * 4 - 2)).astype(dt)
+    if dt.kind == 'u':
+        return rs.randint(0, 7, size=shape).astype(dt)
+    return rs.randint(-3, 4, size=shape).astype(dt)
+
+
+def _rand_view(rs, host, dev):
+    """The same random view (slices with steps, a transpose, maybe a broadcast axis) of a host array and its device twin."""
+    for _ in range(rs.randint(0, 3)):
+        if host.ndim == 0:
+            break
+        kind = rs.randint(0, 3)
+        if kind == 0:
+            key = []
+            for n in host.shape:
+                step = int(rs.choice([1, 1, 2, 3, -1, -2]))
+                lo = int(rs.randint(0, max(n // 2, 1)))
+                key.append(slice(None, None, step) if rs.rand() < 0.5 else
+                           (slice(lo, None, step) if step > 0 else slice(None, lo if lo else None, step)))
+            key = tuple(key)
+            host, dev = host[key], dev[key]
+        elif kind == 1 and host.ndim >= 2:
+            perm = tuple(int(p) for p in rs.permutation(host.ndim))
+            host, dev = host.transpose(perm), dev.transpose(perm)
+        elif kind == 2 and host.ndim >= 1:
+            ax = int(rs.randint(0, host.ndim))
+            key = tuple(slice(0, 1) if d == ax else slice(None) for d in range(host.ndim))
+            if host.shape[ax] >= 1:
+                host, dev = host[key], dev[key]
+                shape = tuple(4 if d == ax else n for d, n in enumerate(host.shape))
+                host, dev = np.broadcast_to(host, shape), dev.broadcast_to(shape)
+    return host, dev
+
+
+def _tol(dt, terms):
+    dt = np.dtype(dt)
+    eps = {2: 1e-3, 4: 1.2e-7, 8: 2.3e-16}[dt.itemsize]
+    return eps * max(terms, 1) * 8
+
+
+def _check(got, want, terms=1, scale=2.0, what=''):
+    got = got.get() if hasattr(got, 'get') else np.asarray(got)
+    want = np.asarray(want)
+    assert got.shape == want.shape, '%s: shape %s vs %s' % (what, got.shape, want.shape)
+    assert got.dtype == want.dtype, '%s: dtype %s vs %s' % (what, got.dtype, want.dtype)
+    if want.dtype.kind == 'f':
+        np.testing.assert_allclose(got.astype('f8'), want.astype('f8'), rtol=_tol(want.dtype, 1),
+                                   atol=_tol(want.dtype, terms) * scale, err_msg=what, equal_nan=True)
+    else:
+        np.testing.assert_array_equal(got, want, err_msg=what)
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_fuzz_reductions(cp, seed):
+    rs = np.random.RandomState(1000 + seed)
+    for case in range(60):
+        dt = DTYPES[rs.randint(len(DTYPES))]
+        base = _rand_data(rs, _rand_shape(rs, big=case % 5 == 0), dt)
+        h, d = _rand_view(rs, base, cp.asarray(base))
+        if h.ndim == 0:
+            axis = None
+        else:
+            k = rs.randint(0, h.ndim + 1)
+            axis = None if k == 0 else tuple(sorted(int(a) for a in rs.choice(h.ndim, size=k, replace=False)))
+            if axis is not None and len(axis) == 1 and rs.rand() < 0.5:
+                axis = axis[0] - (h.ndim if rs.rand() < 0.3 else 0)
+        keep = bool(rs.rand() < 0.3)
+        red = h.shape if axis is None else [h.shape[a] for a in (axis if isinstance(axis, tuple) else (axis,))]
+        terms = int(np.prod(red, dtype=np.int64))
+        what = 'seed %d case %d: %s %s strides %s axis=%r keepdims=%r' % (seed, case, dt, h.shape, h.strides, axis, keep)
+        for name in ('sum', 'prod', 'max', 'min', 'mean', 'var', 'any', 'all', 'argmax', 'argmin'):
+            w = what + ' ' + name
+            kw = {'axis': axis, 'keepdims': keep}
+            if name in ('argmax', 'argmin'):
+                if isinstance(axis, tuple):
+                    continue
+                if h.dtype.kind == 'f' and terms and rs.rand() < 0.3:
+                    pass
+            if name in ('max', 'min', 'argmax', 'argmin') and terms == 0:
+                with pytest.raises(ValueError):
+                    getattr(d, name)(**kw)
+                continue
+            if name in ('mean', 'var') and (terms == 0 or h.size == 0):
+                continue                                   # NumPy warns and returns NaN; covered by the enumerated tests
+            if name == 'prod' and h.dtype.kind == 'f' and terms > 64:
+                continue                                   # products of many U[-2,2) values under/overflow: not a parity case
+            want = getattr(h, name)(**kw)
+            got = getattr(d, name)(**kw)
+            scale = 2.0 if name != 'prod' else float(2.0 ** min(terms, 64))
+            if name == 'var':
+                scale = 8.0
+            _check(got, want, terms, scale, w)
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_fuzz_scans(cp, seed):
+    rs = np.random.RandomState(2000 + seed)
+    for case in range(60):
+        dt = DTYPES[rs.randint(len(DTYPES))]
+        base = _rand_data(rs, _rand_shape(rs, big=case % 4 == 0), dt)
+        h, d = _rand_view(rs, base, cp.asarray(base))
+        axis = None if (h.ndim == 0 or rs.rand() < 0.3) else int(rs.randint(-h.ndim, h.ndim))
+        what = 'seed %d case %d: %s %s strides %s axis=%r' % (seed, case, dt, h.shape, h.strides, axis)
+        n = h.size if axis is None else h.shape[axis]
+        _check(cp.cumsum(d, axis=axis), np.cumsum(h, axis=axis), n, 2.0, what + ' cumsum')
+        if h.dtype.kind != 'f' or n <= 32:
+            small = h if h.dtype.kind != 'f' else h
+            _check(cp.cumprod(d, axis=axis), np.cumprod(small, axis=axis), n, float(2.0 ** min(n, 32)), what + ' cumprod')
+        if rs.rand() < 0.3 and h.dtype.kind in 'iu':
+            odt = np.dtype(rs.choice(['int32', 'int64', 'float64']))
+            _check(cp.cumsum(d, axis=axis, dtype=odt), np.cumsum(h, axis=axis, dtype=odt), n, 2.0, what + ' cumsum dtype=%s' % odt)
+        if rs.rand() < 0.3:
+            want = np.cumsum(h, axis=axis)
+            out = cp.empty(want.shape, want.dtype)
+            r = cp.cumsum(d, axis=axis, out=out)
+            assert r is out
+            _check(out, want, n, 2.0, what + ' cumsum out=')
+
+
+_BINARY = ['add', 'subtract', 'multiply', 'maximum', 'minimum', 'greater', 'less_equal', 'equal', 'true_divide']
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_fuzz_elementwise(cp, seed):
+    rs = np.random.RandomState(3000 + seed)
+    for case in range(80):
+        dta, dtb = DTYPES[rs.randint(len(DTYPES))], DTYPES[rs.randint(len(DTYPES))]
+        shape = _rand_shape(rs, big=case % 6 == 0)
+        a = _rand_data(rs, shape, dta)
+        # b: same shape, a trailing-suffix shape (broadcast), or a python scalar
+        pick = rs.randint(0, 4)
+        if pick == 0 and shape:
+            b = _rand_data(rs, shape[int(rs.randint(0, len(shape))):], dtb)
+        elif pick == 1:
+            b = None
+        else:
+            b = _rand_data(rs, shape, dtb)
+        ha, da = _rand_view(rs, a, cp.asarray(a))
+        if b is None:
+            hb = db = [2, 3.5, True, -1][rs.randint(4)]
+        else:
+            hb, db = b, cp.asarray(b)
+            if hb.shape == a.shape and ha.shape != a.shape:
+                hb, db = _rand_data(rs, ha.shape, dtb), None
+                db = cp.asarray(hb)
+        name = _BINARY[rs.randint(len(_BINARY))]
+        what = 'seed %d case %d: %s(%s %s strides %s, %s)' % (
+            seed, case, name, dta, ha.shape, ha.strides, ('%s %s' % (dtb, hb.shape)) if b is not None else repr(hb))
+        f_np, f_cp = getattr(np, name), getattr(cp, name)
+        try:
+            with np.errstate(all='ignore'):
+                want = f_np(ha, hb)
+        except (TypeError, OverflowError, ValueError) as e:        # bool subtract, out-of-range python int, bad broadcast
+            with pytest.raises(type(e)):
+                f_cp(da, db)
+            continue
+        got = f_cp(da, db)
+        if name == 'true_divide':
+            g, w = got.get(), np.asarray(want)
+            assert g.dtype == w.dtype and g.shape == w.shape, what
+            np.testing.assert_allclose(g.astype('f8'), w.astype('f8'), rtol=_tol(w.dtype, 1), err_msg=what, equal_nan=True)
+        else:
+            _check(got, want, 1, 0.0, what)                   # IEEE-exact ops: bit-for-bit
+        # unary + copy / astype on the same view
+        if rs.rand() < 0.4:
+            _check(da.copy(), ha.copy(), 1, 0.0, what + ' copy')
+            tdt = DTYPES[rs.randint(len(DTYPES))]
+            if not (ha.dtype.kind == 'f' and np.dtype(tdt).kind in 'iub'):   # float -> int of negatives/NaN is UB in C
+                with np.errstate(all='ignore'):
+                    _check(da.astype(tdt), ha.astype(tdt), 1, 0.0, what + ' astype ' + tdt)
+            if ha.dtype.kind != 'b':
+                _check(cp.negative(da), np.negative(ha), 1, 0.0, what + ' negative')
