@@ -29,12 +29,12 @@ def _rand_shape(rs, max_ndim=4, big=False):
 def _rand_data(rs, shape, dt):
     dt = np.dtype(dt)
     if dt.kind == 'b':
-        return rs.rand(*shape) < 0.5
+        return np.asarray(rs.rand(*shape) < 0.5)
     if dt.kind == 'f':
-        return ((rs.rand(*shape) * 4 - 2)).astype(dt)
+        return np.asarray(rs.rand(*shape) * 4 - 2).astype(dt)
     if dt.kind == 'u':
-        return rs.randint(0, 7, size=shape).astype(dt)
-    return rs.randint(-3, 4, size=shape).astype(dt)
+        return np.asarray(rs.randint(0, 7, size=shape)).astype(dt)
+    return np.asarray(rs.randint(-3, 4, size=shape)).astype(dt)
 
 
 def _rand_view(rs, host, dev):
