@@ -818,7 +818,7 @@ def asarray(a, dtype=None, order=None):
         perm = tuple(reversed(range(h.ndim)))
     else:
         perm = tuple(sorted(range(h.ndim), key=lambda i: (-abs(h.strides[i]), i)))
-    hp = numpy.ascontiguousarray(h.transpose(perm))
+    hp = numpy.asarray(h.transpose(perm), order='C')     # (ascontiguousarray would turn 0-d into 1-d)
     dev = ndarray(hp.shape, hp.dtype)
     if dev.size and not _dryrun.enabled:
         src = torch.from_numpy(hp.reshape(-1).view(numpy.uint8))

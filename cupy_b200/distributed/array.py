@@ -219,7 +219,7 @@ class _EngineBackend:
         return self.cp.full(shape, value, dtype)
 
     def from_host(self, a):
-        return self.cp.asarray(numpy.ascontiguousarray(a))
+        return self.cp.asarray(numpy.asarray(a, order='C'))
 
     def to_host(self, a):
         return a.get()

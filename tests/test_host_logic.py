@@ -578,3 +578,12 @@ def test_ufunc_at_and_reduceat_kernels_compile_for_every_supported_dtype(dry):
         cp.add.at(cp.empty((4, 4), 'float32'), (slice(None), cp.empty((1,), 'int64')), 1.0)
     with pytest.raises(IndexError):
         cp.add.reduceat(cp.empty((10,), 'int32'), [0, 10])
+
+
+def test_asarray_keeps_zero_dimensional_host_arrays_zero_dimensional(dry):
+    """Found by tests/test_fuzz_gpu.py: numpy.ascontiguousarray promotes 0-d to 1-d."""
+    import cupy_b200 as cp
+    a = cp.asarray(np.array(3))
+    assert a.shape == () and a.sum(keepdims=True).shape == () and cp.multiply(a, a).shape == ()
+    assert cp.asarray(np.float32(2.5)).shape == () and cp.asarray(7).shape == ()
+    assert cp.asarray(np.ones((3, 4)).T).strides == (8, 32)         # order 'K' keeps the host layout
