@@ -110,8 +110,20 @@ def test_fuzz_reductions(cp, seed):
                 if h.dtype.kind == 'f' and terms and rs.rand() < 0.3:
                     pass
             if name in ('max', 'min', 'argmax', 'argmin') and terms == 0:
-                with pytest.raises(ValueError):
-                    getattr(d, name)(**kw)
+                # no identity: ValueError -- except that the reference returns an empty result first when the
+                # OUTPUT is empty too (cupy/_core/_reduction.pyx:349-354), where NumPy still raises
+                try:
+                    want = getattr(h, name)(**kw)
+                except ValueError:
+                    want = None
+                if want is None and 0 in [n for i, n in enumerate(h.shape) if not (
+                        axis is None or i in [a % h.ndim for a in (axis if isinstance(axis, tuple) else (axis,))])]:
+                    assert getattr(d, name)(**kw).size == 0, w
+                elif want is None:
+                    with pytest.raises(ValueError):
+                        getattr(d, name)(**kw)
+                else:
+                    _check(getattr(d, name)(**kw), want, 1, 0.0, w)
                 continue
             if name in ('mean', 'var') and (terms == 0 or h.size == 0):
                 continue                                   # NumPy warns and returns NaN; covered by the enumerated tests
@@ -187,7 +199,13 @@ def test_fuzz_elementwise(cp, seed):
             with pytest.raises(type(e)):
                 f_cp(da, db)
             continue
-        got = f_cp(da, db)
+        try:
+            got = f_cp(da, db)
+        except OverflowError:
+            # NumPy 2 answers comparisons with an out-of-range Python int; the reference (PyArray_Pack of the scalar
+            # into the loop's type, cupy/_core/_scalar.pyx:375-379) and this package raise for every ufunc
+            assert b is None and name in ('greater', 'less_equal', 'equal') and ha.dtype.kind in 'ub' and hb == -1, what
+            continue
         if name == 'true_divide':
             g, w = got.get(), np.asarray(want)
             assert g.dtype == w.dtype and g.shape == w.shape, what
