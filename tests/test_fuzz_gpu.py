@@ -221,3 +221,104 @@ def test_fuzz_elementwise(cp, seed):
                     _check(da.astype(tdt), ha.astype(tdt), 1, 0.0, what + ' astype ' + tdt)
             if ha.dtype.kind != 'b':
                 _check(cp.negative(da), np.negative(ha), 1, 0.0, what + ' negative')
+
+
+def _rand_expr(rs, depth, n_in):
+    """A random expression tree over inputs x0..x{n-1} and small constants, as source text valid for both modules."""
+    if depth == 0 or rs.rand() < 0.2:
+        return 'x%d' % rs.randint(n_in) if rs.rand() < 0.8 else str(int(rs.randint(1, 4)))
+    kind = rs.randint(0, 8)
+    a, b = _rand_expr(rs, depth - 1, n_in), _rand_expr(rs, depth - 1, n_in)
+    if kind <= 2:
+        return '(%s %s %s)' % (a, '+-*'[kind], b)
+    if kind == 3:
+        return 'xp.maximum(%s, %s)' % (a, b)
+    if kind == 4:
+        return 'xp.minimum(%s, %s)' % (a, b)
+    if kind == 5:
+        return 'xp.negative(%s)' % a if not a.isdigit() else a
+    if kind == 6:
+        return 'xp.absolute(%s)' % a if not a.isdigit() else a
+    return 'xp.square(%s)' % a if not a.isdigit() else a
+
+
+@pytest.mark.parametrize('seed', range(3))
+def test_fuzz_fusion_expression_trees(cp, seed):
+    """cupy_b200.fuse of random expression trees (optionally closed by a reduction) against the same Python function
+    on NumPy arrays -- fusion_utils.check_fusion in the reference's fusion tests.  Integer trees are bit-exact;
+    floating trees may contract a*b+c into one FMA inside the fused kernel, so they get a relative tolerance."""
+    rs = np.random.RandomState(4000 + seed)
+    for case in range(25):
+        n_in = int(rs.randint(1, 4))
+        dt = ['int32', 'int64', 'float32', 'float64', 'int16'][rs.randint(5)]
+        shape = tuple(int(rs.choice([1, 3, 17, 64, 130])) for _ in range(rs.randint(1, 4)))
+        expr = _rand_expr(rs, 4, n_in)
+        if 'x' not in expr:
+            expr = '(x0 + %s)' % expr
+        reduce_axis = None
+        tail = rs.randint(0, 4)
+        if tail == 0:
+            reduce_axis = int(rs.randint(0, len(shape)))
+            expr = 'xp.sum(%s, axis=%d)' % (expr, reduce_axis)
+        elif tail == 1:
+            expr = 'xp.sum(%s)' % expr
+        src = 'def f(%s):\n    return %s\n' % (', '.join('x%d' % i for i in range(n_in)), expr)
+        env_np, env_cp = {'xp': np}, {'xp': cp}
+        exec(src, env_np)
+        exec(src, env_cp)
+        hs = []
+        for i in range(n_in):
+            sh = shape if (i == 0 or rs.rand() < 0.6) else shape[int(rs.randint(0, len(shape))):]
+            hs.append(_rand_data(rs, sh, dt))
+        ds = [cp.asarray(h) for h in hs]
+        what = 'seed %d case %d: %s %s  %s' % (seed, case, dt, [h.shape for h in hs], expr)
+        with np.errstate(all='ignore'):
+            want = np.asarray(env_np['f'](*hs))
+        fused = cp.fuse(kernel_name='fuzz_%d_%d' % (seed, case))(env_cp['f'])
+        got = fused(*ds)
+        plain = env_cp['f'](*ds)                                # the same function launch by launch
+        g, p = got.get(), plain.get()
+        assert g.shape == want.shape and g.dtype == want.dtype, what
+        if want.dtype.kind == 'f':
+            mag = float(np.abs(want.astype('f8')).max()) if want.size else 1.0
+            np.testing.assert_allclose(g.astype('f8'), want.astype('f8'), rtol=1e-4, atol=1e-5 * max(mag, 1.0), err_msg=what)
+            np.testing.assert_allclose(p.astype('f8'), want.astype('f8'), rtol=1e-4, atol=1e-5 * max(mag, 1.0), err_msg=what)
+        else:
+            np.testing.assert_array_equal(g, want, err_msg=what)
+            np.testing.assert_array_equal(p, want, err_msg=what)
+        got2 = fused(*ds)                                        # second call: memoised kernel, same answer
+        np.testing.assert_array_equal(got2.get(), g, err_msg=what)
+
+
+@pytest.mark.parametrize('seed', range(2))
+def test_fuzz_user_kernels(cp, seed):
+    """ElementwiseKernel / ReductionKernel with generic types over random views and broadcasts: an axpy-like
+    elementwise body and an L1-distance reduction, against NumPy."""
+    rs = np.random.RandomState(5000 + seed)
+    ew = cp.ElementwiseKernel('T x, T y, T a', 'T z', 'z = a * x + y', 'fuzz_axpy')
+    l1 = cp.ReductionKernel('T x, T y', 'T z', 'abs(x - y)', 'a + b', 'z = a', '0', 'fuzz_l1')
+    for case in range(40):
+        dt = ['int32', 'int64', 'float32', 'float64'][rs.randint(4)]
+        shape = _rand_shape(rs, max_ndim=3, big=case % 5 == 0)
+        a, b = _rand_data(rs, shape, dt), _rand_data(rs, shape, dt)
+        ha, da = _rand_view(rs, a, cp.asarray(a))
+        hb = _rand_data(rs, ha.shape, dt)
+        if ha.ndim and rs.rand() < 0.3:
+            hb = hb[(0,) * int(rs.randint(1, ha.ndim + 1))]      # a trailing-suffix shape: broadcast
+        db = cp.asarray(hb)
+        what = 'seed %d case %d: %s %s strides %s with %s' % (seed, case, dt, ha.shape, ha.strides, hb.shape)
+        s = np.dtype(dt).type(2)
+        want = s * ha + hb
+        got = ew(da, db, s)
+        if np.dtype(dt).kind == 'f':
+            np.testing.assert_allclose(got.get(), want, rtol=1e-6 if dt == 'float32' else 1e-14, atol=1e-6, err_msg=what)
+        else:
+            np.testing.assert_array_equal(got.get(), want, err_msg=what)
+        if ha.ndim == 0 or ha.size == 0:
+            continue
+        axis = int(rs.randint(0, ha.ndim))
+        hbb = np.broadcast_to(hb, ha.shape)
+        want = np.abs(ha - hbb).sum(axis=axis).astype(dt)
+        got = l1(da, db.broadcast_to(ha.shape) if db.shape != ha.shape else db, axis=axis)
+        terms = ha.shape[axis]
+        _check(got, want, terms, 4.0, what + ' l1 axis=%d' % axis)
