@@ -40,6 +40,7 @@ class _Var:
         self.param_index = param_index
         self.param_name = name if param_index is not None else None   # `name` follows in-place updates
         self.reduced = False
+        self.used = False             # read by some recorded operation, returned, or reduced
 
     # ---- the subset of the ndarray surface a fused function may touch
     def _bin(self, uf, other, swap=False):
@@ -143,6 +144,7 @@ class _Trace:
                 raise ValueError('value belongs to another fused function')
             if a.reduced:
                 raise NotImplementedError('the result of the reduction cannot be used inside the fused function')
+            a.used = True
             return a.name, a.dtype, a.weak_t, a.is_array, a.ndim
         if isinstance(a, ndarray):
             raise TypeError('arrays must be passed to a fused function as arguments, not captured from outside')
@@ -228,6 +230,7 @@ class _Trace:
             raise NotImplementedError('out= of a reduction inside a fused function')
         if not a.is_array:
             raise TypeError('reduction of a scalar inside a fused function')
+        a.used = True
         self.reduction = (kernel, a, axis, dtype, keepdims)
         r = _Var(self, '_reduced', a.dtype, True, 0)
         r.reduced = True
@@ -269,7 +272,12 @@ class _FusedKernel:
         for r in rets:
             if not isinstance(r, _Var):
                 raise TypeError('a fused function must return values computed from its arguments (got %r)' % (r,))
-        in_decl = ', '.join('%s %s' % (p.dtype.name, p.param_name) for p in trace.params)   # parameter types are NumPy names
+            r.used = True
+        # arguments the function never reads or updates stay out of the kernel: they must not take part in the
+        # broadcast that shapes the loop (`lambda x, y: y * y` has y's shape)
+        self.used = [k for k, p in enumerate(trace.params) if p.used or k in trace.assigned]
+        self.used_params = [trace.params[k] for k in self.used]
+        in_decl = ', '.join('%s %s' % (p.dtype.name, p.param_name) for p in self.used_params)   # NumPy type names
         preamble = '\n'.join(trace.preambles)
         body = '\n'.join(trace.steps)
         self.inplace = sorted(trace.assigned.items())
@@ -315,8 +323,8 @@ class _FusedKernel:
         out_t = op.out_types[0]
         if reduce_type is None:
             reduce_type = get_typename(out_t)
-        args_decl = ', '.join('const %s& %s' % (get_typename(p.dtype), p.param_name) for p in trace.params)
-        args_call = ', '.join(p.param_name for p in trace.params)
+        args_decl = ', '.join('const %s& %s' % (get_typename(p.dtype), p.param_name) for p in self.used_params)
+        args_call = ', '.join(p.param_name for p in self.used_params)
         pre = [preamble, kernel.preamble,
                'typedef %s type_in0_raw;' % get_typename(a.dtype),
                'typedef %s type_out0_raw;' % get_typename(out_t),
@@ -381,9 +389,10 @@ class Fusion:
 
 
 def _run(fk, args):
+    targets = [args[pidx] for pidx, _ in fk.inplace]
+    args = [args[k] for k in fk.used]
     if fk.reduction:
         return fk.kernel(*args, axis=fk.red_axis, keepdims=fk.red_keepdims)
-    targets = [args[pidx] for pidx, _ in fk.inplace]
     if fk.n_ret == 0:
         fk.kernel(*args, *targets)
         return None

@@ -587,3 +587,17 @@ def test_asarray_keeps_zero_dimensional_host_arrays_zero_dimensional(dry):
     assert a.shape == () and a.sum(keepdims=True).shape == () and cp.multiply(a, a).shape == ()
     assert cp.asarray(np.float32(2.5)).shape == () and cp.asarray(7).shape == ()
     assert cp.asarray(np.ones((3, 4)).T).strides == (8, 32)         # order 'K' keeps the host layout
+
+
+def test_fused_function_ignores_arguments_it_never_reads(dry):
+    """Found by tests/test_fuzz_gpu.py: an unused (larger) argument must not shape the fused loop."""
+    import cupy_b200 as cp
+    x, y = cp.empty((64, 130), 'i'), cp.empty((130,), 'i')
+    assert cp.fuse(lambda a, b: b * b)(x, y).shape == (130,)
+    assert cp.fuse(lambda a, b: b)(x, y).shape == (130,)
+    assert cp.fuse(lambda a, b: cp.sum(b * 2, axis=0))(x, y).shape == ()
+    assert cp.fuse(lambda a, b, s: a + s)(x, y, 3).shape == (64, 130)
+
+    def upd(a, b):
+        a += 1
+    assert cp.fuse(upd)(x, y) is None and dry[-1]['kind'] in ('jit_elementwise', 'prebuilt_elementwise')
