@@ -3,11 +3,14 @@ unit extents), dtypes, views (steps, negative steps, transposes, broadcasts), ax
 reference's `testing.numpy_cupy_*` decorators compare every routine (tests/cupy_tests/math_tests/test_sumprod.py,
 core_tests/test_ndarray_reduction.py, core_tests/test_ufunc_methods.py), but generated rather than enumerated.
 Integer / bool / index results are bit-exact; floating results within a bound scaled by the reduced magnitude."""
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
+_MORE = int(os.environ.get('B200_FUZZ_MORE', '1'))     # one-off deeper runs: multiplies the number of seeds
 DTYPES = ['bool', 'int8', 'uint8', 'int16', 'int32', 'uint32', 'int64', 'uint64', 'float16', 'float32', 'float64']
 
 
@@ -83,7 +86,7 @@ def _check(got, want, terms=1, scale=2.0, what=''):
         np.testing.assert_array_equal(got, want, err_msg=what)
 
 
-@pytest.mark.parametrize('seed', range(6))
+@pytest.mark.parametrize('seed', range(6 * _MORE))
 def test_fuzz_reductions(cp, seed):
     rs = np.random.RandomState(1000 + seed)
     for case in range(60):
@@ -137,7 +140,7 @@ def test_fuzz_reductions(cp, seed):
             _check(got, want, terms, scale, w)
 
 
-@pytest.mark.parametrize('seed', range(4))
+@pytest.mark.parametrize('seed', range(4 * _MORE))
 def test_fuzz_scans(cp, seed):
     rs = np.random.RandomState(2000 + seed)
     for case in range(60):
@@ -165,7 +168,7 @@ def test_fuzz_scans(cp, seed):
 _BINARY = ['add', 'subtract', 'multiply', 'maximum', 'minimum', 'greater', 'less_equal', 'equal', 'true_divide']
 
 
-@pytest.mark.parametrize('seed', range(4))
+@pytest.mark.parametrize('seed', range(4 * _MORE))
 def test_fuzz_elementwise(cp, seed):
     rs = np.random.RandomState(3000 + seed)
     for case in range(80):
@@ -242,7 +245,7 @@ def _rand_expr(rs, depth, n_in):
     return 'xp.square(%s)' % a if not a.isdigit() else a
 
 
-@pytest.mark.parametrize('seed', range(3))
+@pytest.mark.parametrize('seed', range(3 * _MORE))
 def test_fuzz_fusion_expression_trees(cp, seed):
     """cupy_b200.fuse of random expression trees (optionally closed by a reduction) against the same Python function
     on NumPy arrays -- fusion_utils.check_fusion in the reference's fusion tests.  Integer trees are bit-exact;
@@ -293,7 +296,7 @@ def test_fuzz_fusion_expression_trees(cp, seed):
         np.testing.assert_array_equal(got2.get(), g, err_msg=what)
 
 
-@pytest.mark.parametrize('seed', range(2))
+@pytest.mark.parametrize('seed', range(2 * _MORE))
 def test_fuzz_user_kernels(cp, seed):
     """ElementwiseKernel / ReductionKernel with generic types over random views and broadcasts: an axpy-like
     elementwise body and an L1-distance reduction, against NumPy."""
