@@ -4,6 +4,7 @@ reference's `testing.numpy_cupy_*` decorators compare every routine (tests/cupy_
 core_tests/test_ndarray_reduction.py, core_tests/test_ufunc_methods.py), but generated rather than enumerated.
 Integer / bool / index results are bit-exact; floating results within a bound scaled by the reduced magnitude."""
 import os
+import re
 
 import numpy as np
 import pytest
@@ -133,6 +134,12 @@ def test_fuzz_reductions(cp, seed):
             if name == 'prod' and h.dtype.kind == 'f' and terms > 64:
                 continue                                   # products of many U[-2,2) values under/overflow: not a parity case
             want = getattr(h, name)(**kw)
+            if name in ('var', 'mean') and h.dtype == np.float16:
+                # NumPy's float16 intermediates overflow past 65504; the reference accumulates float16 in float
+                # (cupy/_core/_routines_statistics.pyx:611-616, 647-655), as the kernels here do
+                want = np.asarray(getattr(h.astype(np.float32), name)(**kw)).astype(np.float16)
+                if not keep and want.ndim == 0:
+                    want = want[()]
             got = getattr(d, name)(**kw)
             scale = 2.0 if name != 'prod' else float(2.0 ** min(terms, 64))
             if name == 'var':
@@ -199,6 +206,9 @@ def test_fuzz_elementwise(cp, seed):
             with np.errstate(all='ignore'):
                 want = f_np(ha, hb)
         except (TypeError, OverflowError, ValueError) as e:        # bool subtract, out-of-range python int, bad broadcast
+            if isinstance(e, OverflowError) and 0 in ha.shape:
+                f_cp(da, db)          # the reference returns the empty result before it packs the scalar (_kernel.pyx:1385-1392)
+                continue
             with pytest.raises(type(e)):
                 f_cp(da, db)
             continue
@@ -256,7 +266,7 @@ def test_fuzz_fusion_expression_trees(cp, seed):
         dt = ['int32', 'int64', 'float32', 'float64', 'int16'][rs.randint(5)]
         shape = tuple(int(rs.choice([1, 3, 17, 64, 130])) for _ in range(rs.randint(1, 4)))
         expr = _rand_expr(rs, 4, n_in)
-        if 'x' not in expr:
+        if not re.search(r'x\d', expr):
             expr = '(x0 + %s)' % expr
         reduce_axis = None
         tail = rs.randint(0, 4)
