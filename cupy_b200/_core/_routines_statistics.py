@@ -195,6 +195,14 @@ _var_core_out = ReductionKernel(
     'S x, T mean, U alpha', 'U out', 'my_norm(x - mean)', 'a + b', 'out = alpha * a', '0',
     'cupy_var_core_out', preamble=_norm_preamble)
 
+# float16 results: the reference's `_var_core_float16` (:611-616) accumulates the squared deviations in float16 and
+# overflows to inf past 65504 (as NumPy does); here they are accumulated in float -- the same arithmetic as the
+# single-pass functor, so the answer does not depend on which layout route a call takes
+_var_core_float16 = ReductionKernel(
+    'S x, T mean, float32 alpha', 'float16 out',
+    'my_norm(static_cast<float>(x) - static_cast<float>(mean))', 'a + b', 'out = alpha * a', '0',
+    'cupy_var_core_float16', reduce_type='float', preamble=_norm_preamble)
+
 _var_types = ('?->d', 'b->d', 'B->d', 'h->d', 'H->d', 'i->d', 'I->d', 'l->d', 'L->d', 'q->d', 'Q->d',
               'e->e', 'f->f', 'd->d')
 
@@ -264,6 +272,8 @@ def _var(a, axis=None, dtype=None, out=None, ddof=0, keepdims=False):
     div = max(items - ddof, 0)
     alpha = 1. / div if div != 0 else math.nan
     arrmean = a.mean(axis=axis, dtype=dtype_mean, out=None, keepdims=True)
+    if out is None and dtype_out == numpy.float16:
+        return _var_core_float16(a, arrmean, numpy.float32(alpha), axis=axis, keepdims=keepdims)
     if out is None:
         res = ndarray(_out_shape(a.shape, reduce_axis, out_axis, keepdims), dtype_out)
         _var_core_out(a, arrmean, numpy.asarray(alpha, dtype=dtype_out)[()], res, axis=axis, keepdims=keepdims)
