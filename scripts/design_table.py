@@ -23,14 +23,19 @@ def main():
         print('|---|---|---|---|---|---|---|')
         for e in n1.get('configs', []):
             if 'ms' not in e:
-                print('| %s | host %.1f us / call (sum), %.1f us (add); GPU %.1f us | | | %s | %s | |' % (
+                print('| %s | host %.1f us / call (sum), %.1f us (add); with an event pair per call %.1f us; in a CUDA graph %s us | | | %s | %s | |' % (
                     e['name'], e['host_us_per_call_sum'], e['host_us_per_call_add'], e['gpu_us_per_call_sum'],
+                    ('%.1f' % e['graph_replay_us_sum']) if e.get('graph_replay_us_sum') is not None else '-',
                     e['check'], e.get('reference_documented', '')))
                 continue
             r = e.get('ref_gpu') or {}
             ref = ('%.3f ms, %.0f GB/s' % (r['ms'], r['gbs'])) if 'ms' in r else (r.get('skipped') or r.get('error') or '')
+            name = e['name']
+            if e.get('graph_replay_us') is not None:
+                name += ' -- host-bound per call; the kernel alone, replayed in a CUDA graph: %.1f us = %.0f GB/s (%.0f %%)' % (
+                    e['graph_replay_us'], e['graph_replay_gbs'], 100 * e['graph_replay_frac'])
             print('| %s | %.3f | %.0f | %.1f | %s | %s | %s |' % (
-                e['name'], e['ms'], e['gbs'], 100 * e['frac'], e['check'], ref,
+                name, e['ms'], e['gbs'], 100 * e['frac'], e['check'], ref,
                 ('%.2fx' % e['speedup_vs_ref_gpu']) if 'speedup_vs_ref_gpu' in e else ''))
         c1 = n1.get('c1_cpu')
         if c1:
