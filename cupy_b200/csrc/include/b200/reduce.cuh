@@ -55,6 +55,22 @@ B200_DEVICE T load_volatile(const T* p) {
     return u.t;
 }
 
+// The same for data whose publication the caller has already ordered (ticket + fences): L2 loads (ld.global.cg,
+// around the non-coherent L1) in the widest words the type allows, NOT volatile, so independent loads can be
+// batched ahead of their uses.  `p` must be aligned to that word (16 / 8 / 4 bytes).
+template <class T>
+B200_DEVICE T load_cg(const T* p) {
+    constexpr int wbytes = (sizeof(T) % 16 == 0) ? 16 : (sizeof(T) % 8 == 0) ? 8 : (sizeof(T) % 4 == 0) ? 4 : 1;
+    typedef typename RawVec<wbytes>::type W;
+    constexpr int words = sizeof(T) / sizeof(W);
+    union U { T t; W w[words]; B200_DEVICE U() {} };
+    U u;
+    const W* s = reinterpret_cast<const W*>(p);
+#pragma unroll
+    for (int i = 0; i < words; ++i) u.w[i] = __ldcg(s + i);
+    return u.t;
+}
+
 // Sub-warp combine over GROUP consecutive lanes; result valid in the group's lane 0.
 template <int GROUP, class Op, class T>
 B200_DEVICE T group_combine(const Op& op, T v) {
@@ -420,12 +436,56 @@ __device__ __forceinline__ void reduce_cols_body(
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // The last block of the tile folds the splits.  Threads are laid out as (pack of VEC columns) x (kLanes
+    // split lanes): each thread folds every kLanes-th split of its pack with vector L2 loads, several
+    // independent loads in flight -- a serial walk would be one dependent L2 round trip per split, which is what
+    // bounds L2-resident and tall-narrow matrices -- and the split lanes meet through shared memory.
+    constexpr int kQuads = kBlockCols / VEC;              // WC * 32 packs across the tile
+    constexpr int kLanes = kWarps * 32 / kQuads;          // == kWarpRows
+    struct Q { acc_t v[VEC]; };
+    constexpr int kBatch = sizeof(Q) <= 16 ? 8 : (sizeof(Q) <= 32 ? 4 : 2);
+    const int q = threadIdx.x % kQuads, g = threadIdx.x / kQuads;
+    const int64_t c = tile_c0 + int64_t(q) * VEC;
+    const bool live = c < cols && g < nsplit;             // VEC > 1 => cols % VEC == 0 => whole pack in range
+    Q a;
+    if (live) {
+        const acc_t* col = partials + (b * nsplit) * cols + c;
+        a = load_cg(reinterpret_cast<const Q*>(col + int64_t(g) * cols));
+        int s = g + kLanes;
+        for (; s + (kBatch - 1) * kLanes < nsplit; s += kBatch * kLanes) {
+            Q v[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) v[k] = load_cg(reinterpret_cast<const Q*>(col + int64_t(s + k * kLanes) * cols));
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) a.v[e] = op.combine(a.v[e], v[k].v[e]);
+            }
+        }
+        for (; s < nsplit; s += kLanes) {
+            const Q v = load_cg(reinterpret_cast<const Q*>(col + int64_t(s) * cols));
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) a.v[e] = op.combine(a.v[e], v.v[e]);
+        }
+    }
+    if (kLanes == 1) {
+        if (live) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) y[b * cols + c + e] = op.post(a.v[e], n);
+        }
+        return;
+    }
+    if (live) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) smem[g][q * VEC + e] = a.v[e];
+    }
+    __syncthreads();
+    const int groups = nsplit < kLanes ? nsplit : kLanes;
     for (int t = threadIdx.x; t < kBlockCols; t += blockDim.x) {
         if (tile_c0 + t >= cols) continue;
-        acc_t a = load_volatile(partials + (b * nsplit) * cols + tile_c0 + t);
-        for (int s = 1; s < nsplit; ++s)
-            a = op.combine(a, load_volatile(partials + (b * nsplit + s) * cols + tile_c0 + t));
-        y[b * cols + tile_c0 + t] = op.post(a, n);
+        acc_t r = smem[0][t];
+        for (int w = 1; w < groups; ++w) r = op.combine(r, smem[w][t]);
+        y[b * cols + tile_c0 + t] = op.post(r, n);
     }
 }
 

@@ -118,7 +118,8 @@ static void cols_geometry(int64_t batch, int64_t n, int64_t cols, int vec, int s
     const int64_t tiles = (cols + block_cols - 1) / block_cols;
     // enough blocks for ~8 per SM, at least 64 rows per split
     int64_t want = (int64_t(sm) * 8 + tiles * batch - 1) / (tiles * batch);
-    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>(want, n / 64));
+    static const int min_rows = [] { const char* e = getenv("B200_COLS_MIN_ROWS"); return e && atoi(e) > 0 ? atoi(e) : 64; }();   // A/B knob
+    int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>(want, n / min_rows));
     nsplit = std::min<int64_t>(nsplit, 65535);
     g->gx = unsigned(tiles);
     g->gy = unsigned(nsplit);
@@ -247,6 +248,8 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
         const size_t pbytes = g.partial_count * sizeof(acc_t);
         if (g.partial_count && ws_bytes < kTicketBytes + pbytes)
             return fail(B200_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, kTicketBytes + pbytes);
+        if (g.partial_count && (reinterpret_cast<uintptr_t>(ws) & 15))
+            return fail(B200_E_INVALID, "workspace must be 16-byte aligned (vector loads of the split partials)");
         uint32_t* tickets = static_cast<uint32_t*>(ws);
         acc_t* partials = reinterpret_cast<acc_t*>(static_cast<char*>(ws) + kTicketBytes);
         const dim3 grid(g.gx, g.gy, g.gz);

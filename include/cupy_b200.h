@@ -202,7 +202,7 @@ typedef struct b200_reduce_desc {
 
 int b200_reduce_supported(const b200_reduce_desc_t* d);
 int b200_reduce_workspace_bytes(const b200_reduce_desc_t* d, size_t* bytes);
-/* workspace must be zero-filled once when it is allocated; kernels leave it zeroed */
+/* workspace must be 16-byte aligned and zero-filled once when it is allocated; kernels leave it zeroed */
 int b200_reduce_run(const b200_reduce_desc_t* d, const void* x, void* y,
                     void* workspace, size_t workspace_bytes, void* stream);
 
