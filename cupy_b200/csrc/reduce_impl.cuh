@@ -6,6 +6,7 @@
 // cupy/_core/_reduction.pyx:239-253, 481-508; op / dtype codes are the
 // reference's (cupy_cub.h:4-11, type_dispatcher.cuh:15-28).
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -120,6 +121,14 @@ static void cols_geometry(int64_t batch, int64_t n, int64_t cols, int vec, int s
     int64_t want = (int64_t(sm) * 8 + tiles * batch - 1) / (tiles * batch);
     static const int min_rows = [] { const char* e = getenv("B200_COLS_MIN_ROWS"); return e && atoi(e) > 0 ? atoi(e) : 64; }();   // A/B knob
     int64_t nsplit = std::max<int64_t>(1, std::min<int64_t>(want, n / min_rows));
+    // one strip per block (8 split lanes in the fold): the fold by the tile's last block costs ~ nsplit / 8 batched
+    // L2 round trips, the main loop ~ n / (nsplit * 8 * unroll); past nsplit ~ sqrt(n) the fold is the longer of the
+    // two (tall, narrow matrices: (65536, 256) var went 48 -> see profiles/r02_cols_probe.log)
+    static const bool sqrt_cap = getenv("B200_COLS_NO_SQRT_CAP") == nullptr;      // A/B knob
+    if (sqrt_cap && cols_wc(cols, vec, heavy) == 1 && nsplit > 1) {
+        const int64_t cap = std::max<int64_t>(int64_t(std::sqrt(double(n))), (2 * int64_t(sm) + tiles * batch - 1) / (tiles * batch));
+        nsplit = std::max<int64_t>(1, std::min<int64_t>(nsplit, cap));
+    }
     nsplit = std::min<int64_t>(nsplit, 65535);
     g->gx = unsigned(tiles);
     g->gy = unsigned(nsplit);

@@ -9,7 +9,8 @@ import torch  # noqa: E402
 import cupy_b200 as cp  # noqa: E402
 from bench_configs import _graph_us  # noqa: E402
 
-for shape in ((4096, 4096), (1024, 16384), (16384, 1024), (8192, 8192), (2048, 2048), (512, 512), (65536, 256)):
+for shape in ((4096, 4096), (1024, 16384), (16384, 1024), (8192, 8192), (2048, 2048), (512, 512), (65536, 256),
+              (262144, 128), (1 << 20, 64), (1 << 22, 64), (1 << 20, 256), (30000, 1000)):
     t = torch.rand(*shape, device='cuda') * 2 - 1
     x = cp.from_torch(t)
     nbytes = 4 * shape[0] * shape[1]
