@@ -490,6 +490,124 @@ __device__ __forceinline__ void reduce_cols_body(
 }
 
 // ---------------------------------------------------------------------------
+// COLS, narrow: x[n][cols] whose rows are no longer than one strip (cols <= 128 elements: point clouds,
+// feature tables).  The strip kernel above leaves most lanes of a warp without a column there; this one reads
+// the matrix as the flat stream it is -- grid-stride 16-byte loads, the FULL reduction's access pattern -- with
+// `active` threads per block, chosen by the host so that active * VEC is a multiple of cols: the k-th element of
+// a thread's vector then falls in the same column, (t * VEC + k) % cols, in every chunk, so the thread's VEC
+// lane accumulators ARE column accumulators.  A chunk is active * VEC / cols whole rows; the row handed to the
+// functor is the chunk's first row, and the lane's constant row inside a chunk, (t * VEC + k) / cols, is added
+// to arg-reduction results afterwards (shift_index).  Lanes meet by column through shared memory, blocks
+// through the workspace (gridDim.x * cols partials + the self-resetting ticket); every fold order is fixed.
+// ---------------------------------------------------------------------------
+template <class A> B200_DEVICE void shift_index(A&, long long) {}     // overloaded for (value, index) accumulators
+
+// column `c` of `count` row-major rows of accumulators starting at `rows`: the threads of a block are laid out
+// as (column, group); group gi folds rows gi, gi + G, ...; the groups' results then meet in `groups`
+template <class Op, int THREADS, bool FROM_GLOBAL>
+B200_DEVICE typename Op::acc_t fold_by_column(const Op& op, const typename Op::acc_t* rows, int count, int cols,
+                                              typename Op::acc_t* groups, bool* has_out) {
+    typedef typename Op::acc_t acc_t;
+    const int t = threadIdx.x, G = THREADS / cols;
+    const int c = t % cols, gi = t / cols;
+    const bool has = gi < G && gi < count;
+    if (has) {
+        const acc_t* p = rows + c;
+        acc_t a = FROM_GLOBAL ? load_cg(p + int64_t(gi) * cols) : p[int64_t(gi) * cols];
+        int r = gi + G;
+        if (FROM_GLOBAL) {
+            for (; r + 3 * G < count; r += 4 * G) {
+                acc_t v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = load_cg(p + int64_t(r + k * G) * cols);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a = op.combine(a, v[k]);
+            }
+        }
+        for (; r < count; r += G) a = op.combine(a, FROM_GLOBAL ? load_cg(p + int64_t(r) * cols) : p[int64_t(r) * cols]);
+        groups[gi * cols + c] = a;
+    }
+    __syncthreads();
+    *has_out = t < cols;
+    acc_t r = groups[t < cols ? t : 0];
+    if (t < cols) {
+        const int used = count < G ? count : G;
+        for (int w = 1; w < used; ++w) r = op.combine(r, groups[w * cols + t]);
+    }
+    return r;
+}
+
+template <class Op, int VEC, int UNROLL, int THREADS>
+__device__ __forceinline__ void reduce_narrow_body(
+        const Op& op, typename in_ptr<Op>::type x, typename Op::out_t* __restrict__ y,
+        int64_t n, int cols, int active, typename Op::acc_t* partials, uint32_t* ticket) {
+    typedef typename Op::acc_t acc_t;
+    typedef typename Op::index_t index_t;
+    // raw storage: acc_t may have user constructors
+    __shared__ __align__(16) char lanes_raw[THREADS * VEC * sizeof(acc_t)];
+    __shared__ __align__(16) char groups_raw[THREADS * sizeof(acc_t)];
+    acc_t* lanes = reinterpret_cast<acc_t*>(lanes_raw);
+    acc_t* groups = reinterpret_cast<acc_t*>(groups_raw);
+    __shared__ bool is_last;
+
+    const int t = threadIdx.x;
+    const int chunk_rows = active * VEC / cols;
+    const int64_t chunk_elems = int64_t(active) * VEC;
+    const int64_t chunks = n / chunk_rows;
+    const bool on = t < active;
+
+    if (on) {
+        ThreadAcc<Op, UNROLL, VEC> ta(op);
+        const typename in_ptr<Op>::type xt = x + int64_t(t) * VEC;
+        const int64_t g = gridDim.x;
+        int64_t c = blockIdx.x;
+        for (; c + int64_t(UNROLL - 1) * g < chunks; c += int64_t(UNROLL) * g) {
+            Pack<typename Op::in_t, VEC> v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) load_pack(v[u], xt + (c + int64_t(u) * g) * chunk_elems);
+            ta.fold(v, static_cast<index_t>(c * chunk_rows), static_cast<index_t>(g * chunk_rows), static_cast<index_t>(0));
+        }
+        for (; c < chunks; c += g) {
+            Pack<typename Op::in_t, VEC> v;
+            load_pack(v, xt + c * chunk_elems);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) ta.fold_one_lane(k, v[k], static_cast<index_t>(c * chunk_rows));
+        }
+        if (blockIdx.x == gridDim.x - 1) {                 // the rows past the last whole chunk
+            const int64_t e0 = chunks * chunk_elems + int64_t(t) * VEC, total = n * cols;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                if (e0 + k < total) ta.fold_one_lane(k, x[e0 + k], static_cast<index_t>(chunks * chunk_rows));
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            acc_t a = ta.result_lane(k);
+            shift_index(a, (t * VEC + k) / cols);
+            lanes[t * VEC + k] = a;
+        }
+    }
+    __syncthreads();
+    bool mine;
+    acc_t r = fold_by_column<Op, THREADS, false>(op, lanes, chunk_rows, cols, groups, &mine);
+    if (gridDim.x == 1) {
+        if (mine) y[t] = op.post(r, n);
+        return;
+    }
+    if (mine) partials[int64_t(blockIdx.x) * cols + t] = r;
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        const uint32_t k = atomicInc(ticket, gridDim.x - 1);      // self-resetting
+        is_last = (k == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    r = fold_by_column<Op, THREADS, true>(op, partials, int(gridDim.x), cols, groups, &mine);
+    if (mine) y[t] = op.post(r, n);
+}
+
+// ---------------------------------------------------------------------------
 // GENERIC: any strides, any number of (broadcast) inputs and outputs -- the
 // fallback for layouts that are none of FULL / ROWS / COLS and for user
 // ReductionKernels with several array operands (e.g. the reference's

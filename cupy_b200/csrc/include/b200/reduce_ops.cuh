@@ -66,6 +66,8 @@ template <class V>
 struct ValIdx32 { V value; int index; };
 template <class V>
 struct ValIdx64 { V value; long long index; };
+template <class V> B200_DEVICE void shift_index(ValIdx32<V>& a, long long d) { if (a.index >= 0) a.index += static_cast<int>(d); }
+template <class V> B200_DEVICE void shift_index(ValIdx64<V>& a, long long d) { if (a.index >= 0) a.index += d; }
 template <class V, class I> struct val_idx;
 template <class V> struct val_idx<V, int> { typedef ValIdx32<V> type; };
 template <class V> struct val_idx<V, long long> { typedef ValIdx64<V> type; };

@@ -51,6 +51,13 @@ __global__ void __launch_bounds__(kRedThreads) reduce_cols_kernel(
     reduce_cols_body<Op, VEC, RU, WC>(op, x, y, n, cols, partials, tickets);
 }
 
+template <class Op, int VEC, int UNROLL>
+__global__ void __launch_bounds__(kRedThreads) reduce_narrow_kernel(
+        Op op, const typename Op::in_t* x, typename Op::out_t* y, int64_t n, int cols, int active,
+        typename Op::acc_t* partials, uint32_t* ticket) {
+    reduce_narrow_body<Op, VEC, UNROLL, kRedThreads>(op, x, y, n, cols, active, partials, ticket);
+}
+
 // ---- geometry ---------------------------------------------------------------
 struct Geometry {
     int vec;                 // chosen vector width
@@ -135,6 +142,35 @@ static void cols_geometry(int64_t batch, int64_t n, int64_t cols, int vec, int s
     g->gz = unsigned(batch);
     g->partial_count = nsplit > 1 ? size_t(batch) * nsplit * cols : 0;
     g->ticket_count = nsplit > 1 ? size_t(batch) * tiles : 0;
+}
+
+// narrow COLS (reduce_narrow_body): rows of at most 128 elements, one batch, enough rows to be worth a
+// persistent grid.  Threads that take part per block: the largest count <= 256 whose vectors tile whole rows.
+constexpr int kNarrowMaxCols = 128;
+static bool narrow_shape(const b200_reduce_desc_t* d) {
+    static const bool off = getenv("B200_COLS_NO_NARROW") != nullptr;          // A/B knob
+    return !off && d->batch == 1 && d->n_out >= 1 && d->n_out <= kNarrowMaxCols && d->n_reduce * d->n_out >= 32768
+        && d->n_reduce < (int64_t(1) << 31);
+}
+static int narrow_active(int cols, int vec) {
+    int a = cols, b = vec;
+    while (b) { const int r = a % b; a = b; b = r; }            // a = gcd(cols, vec)
+    const int q = cols / a;
+    return kRedThreads / q * q;
+}
+// widest vector (elements) whose lane accumulators fit 32 KiB of shared memory
+template <class acc_t> constexpr int narrow_vec(int fullvec) {
+    return (fullvec > 1 && size_t(kRedThreads) * fullvec * sizeof(acc_t) > 32768) ? narrow_vec<acc_t>(fullvec / 2) : fullvec;
+}
+template <class Op, int VEC, int UNROLL>
+static int narrow_blocks_per_sm() {
+    static int occ = 0;      // per instantiation; benign race
+    if (!occ) {
+        int o = 0;
+        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, reduce_narrow_kernel<Op, VEC, UNROLL>, kRedThreads, 0);
+        occ = (e == cudaSuccess && o > 0) ? std::min(o, 8) : 4;
+    }
+    return occ;
 }
 
 // which functors may be folded across GPUs by value: everything except the arg-reductions, whose
@@ -244,8 +280,27 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
             cols_geometry(d->batch, d->n_reduce, d->n_out, 1, 296, fast_lanes<Op>::value, &g);
             Geometry g2 = {};
             cols_geometry(d->batch, d->n_reduce, d->n_out, CV, 296, fast_lanes<Op>::value, &g2);
-            const size_t pc = std::max(g.partial_count, g2.partial_count);
+            size_t pc = std::max(g.partial_count, g2.partial_count);
+            if (narrow_shape(d)) pc = std::max(pc, size_t(296) * 8 * size_t(d->n_out));
             *need = pc ? kTicketBytes + align_up(pc * sizeof(acc_t), 16) : 0;
+            return 0;
+        }
+        constexpr int NV = narrow_vec<acc_t>(FULLVEC);
+        if (NV > 1 && narrow_shape(d) && reinterpret_cast<uintptr_t>(x) % (uintptr_t(NV) * sizeof(in_t)) == 0) {
+            const int cols = int(d->n_out);
+            const int active = narrow_active(cols, NV);
+            const int64_t chunks = d->n_reduce / (int64_t(active) * NV / cols);
+            const int grid = int(std::max<int64_t>(1, std::min<int64_t>((chunks + U - 1) / U,
+                                                                         int64_t(di.sm_count) * narrow_blocks_per_sm<Op, NV, U>())));
+            const size_t pbytes = size_t(grid) * cols * sizeof(acc_t);
+            if (grid > 1 && ws_bytes < kTicketBytes + pbytes)
+                return fail(B200_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, kTicketBytes + pbytes);
+            if (grid > 1 && (reinterpret_cast<uintptr_t>(ws) & 15))
+                return fail(B200_E_INVALID, "workspace must be 16-byte aligned");
+            reduce_narrow_kernel<Op, NV, U><<<grid, kRedThreads, 0, stream>>>(
+                op, x, y, d->n_reduce, cols, active, reinterpret_cast<acc_t*>(static_cast<char*>(ws) + kTicketBytes),
+                static_cast<uint32_t*>(ws));
+            B200_CUDA_TRY(cudaPeekAtLastError());
             return 0;
         }
         int vec = pick_vec<CV>(x, d->n_out, sizeof(in_t));
