@@ -490,8 +490,7 @@ __device__ __forceinline__ void reduce_cols_body(
 }
 
 // ---------------------------------------------------------------------------
-// COLS, narrow: x[n][cols] whose rows are no longer than one strip (cols <= 128 elements: point clouds,
-// feature tables).  The strip kernel above leaves most lanes of a warp without a column there; this one reads
+// COLS, narrow: x[n][cols] with short rows (cols <= 64 elements: point clouds, feature tables).  The strip kernel above leaves most lanes of a warp without a column there; this one reads
 // the matrix as the flat stream it is -- grid-stride 16-byte loads, the FULL reduction's access pattern -- with
 // `active` threads per block, chosen by the host so that active * VEC is a multiple of cols: the k-th element of
 // a thread's vector then falls in the same column, (t * VEC + k) % cols, in every chunk, so the thread's VEC
@@ -516,12 +515,13 @@ B200_DEVICE typename Op::acc_t fold_by_column(const Op& op, const typename Op::a
         acc_t a = FROM_GLOBAL ? load_cg(p + int64_t(gi) * cols) : p[int64_t(gi) * cols];
         int r = gi + G;
         if (FROM_GLOBAL) {
-            for (; r + 3 * G < count; r += 4 * G) {
-                acc_t v[4];
+            constexpr int kBatch = sizeof(acc_t) <= 8 ? 8 : 4;       // independent L2 loads in flight
+            for (; r + (kBatch - 1) * G < count; r += kBatch * G) {
+                acc_t v[kBatch];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = load_cg(p + int64_t(r + k * G) * cols);
+                for (int k = 0; k < kBatch; ++k) v[k] = load_cg(p + int64_t(r + k * G) * cols);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) a = op.combine(a, v[k]);
+                for (int k = 0; k < kBatch; ++k) a = op.combine(a, v[k]);
             }
         }
         for (; r < count; r += G) a = op.combine(a, FROM_GLOBAL ? load_cg(p + int64_t(r) * cols) : p[int64_t(r) * cols]);

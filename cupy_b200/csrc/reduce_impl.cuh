@@ -144,9 +144,9 @@ static void cols_geometry(int64_t batch, int64_t n, int64_t cols, int vec, int s
     g->ticket_count = nsplit > 1 ? size_t(batch) * tiles : 0;
 }
 
-// narrow COLS (reduce_narrow_body): rows of at most 128 elements, one batch, enough rows to be worth a
+// narrow COLS (reduce_narrow_body): rows of at most 64 elements, one batch, enough rows to be worth a
 // persistent grid.  Threads that take part per block: the largest count <= 256 whose vectors tile whole rows.
-constexpr int kNarrowMaxCols = 128;
+constexpr int kNarrowMaxCols = 64;       // past it the strip kernel has most lanes busy and fewer partials to fold
 static bool narrow_shape(const b200_reduce_desc_t* d) {
     static const bool off = getenv("B200_COLS_NO_NARROW") != nullptr;          // A/B knob
     return !off && d->batch == 1 && d->n_out >= 1 && d->n_out <= kNarrowMaxCols && d->n_reduce * d->n_out >= 32768
@@ -290,8 +290,11 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
             const int cols = int(d->n_out);
             const int active = narrow_active(cols, NV);
             const int64_t chunks = d->n_reduce / (int64_t(active) * NV / cols);
-            const int grid = int(std::max<int64_t>(1, std::min<int64_t>((chunks + U - 1) / U,
-                                                                         int64_t(di.sm_count) * narrow_blocks_per_sm<Op, NV, U>())));
+            // the last block folds grid * cols partials with 256 / cols threads per column: wider rows get fewer
+            // blocks (never under two per SM) so that this fold stays a few L2 round trips long
+            const int64_t resident = int64_t(di.sm_count) * narrow_blocks_per_sm<Op, NV, U>();
+            const int64_t fold_cap = std::max<int64_t>(2 * int64_t(di.sm_count), 16384 / cols);
+            const int grid = int(std::max<int64_t>(1, std::min<int64_t>((chunks + U - 1) / U, std::min(resident, fold_cap))));
             const size_t pbytes = size_t(grid) * cols * sizeof(acc_t);
             if (grid > 1 && ws_bytes < kTicketBytes + pbytes)
                 return fail(B200_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, kTicketBytes + pbytes);

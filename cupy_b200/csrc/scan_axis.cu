@@ -20,6 +20,7 @@
 #include "common.h"
 #include "include/b200/scan.cuh"
 #include "include/b200/scan_march.cuh"
+#include "include/b200/scan_narrow.cuh"
 #include "tma_host.h"
 #include "scan_table.h"
 
@@ -198,6 +199,53 @@ static int launch_march(const In* x, Out* y, int64_t outer, int64_t n, int64_t i
     return 0;
 }
 
+// ---- tall, narrow matrices (b200/scan_narrow.cuh): flat-stream tiles, reduce-then-scan over one segment per block ----
+template <class In, class Acc, class Out, class Op>
+__global__ void __launch_bounds__(kNarrowScanThreads) scan_narrow_totals_kernel(const In* x, int64_t n, int cols, int active,
+                                                                                int64_t seg_tiles, Acc* tot) {
+    scan_narrow_totals_body<In, Acc, Out, Op>(x, n, cols, active, seg_tiles, tot);
+}
+template <class In, class Acc, class Out, class Op>
+__global__ void __launch_bounds__(kNarrowScanThreads) scan_narrow_kernel(const In* x, Out* y, int64_t n, int cols, int active,
+                                                                         int64_t seg_tiles, const Acc* tot) {
+    scan_narrow_body<In, Acc, Out, Op>(x, y, n, cols, active, seg_tiles, tot);
+}
+
+static bool narrow_scan_shape(int64_t outer, int64_t n, int64_t inner) {
+    static const bool off = getenv("B200_SCAN_NO_NARROW") != nullptr;          // A/B knob
+    return !off && outer == 1 && inner >= 2 && inner <= kNarrowScanMaxCols && n * inner >= 65536;
+}
+constexpr size_t kNarrowScanWorkspace = size_t(296) * 8 * kNarrowScanMaxCols * 8;     // segments x columns x widest accumulator
+
+template <class In, class Acc, class Out, class Op>
+static int launch_narrow(const In* x, Out* y, int64_t n, int cols, void* ws, size_t ws_bytes, int sm_count, cudaStream_t s) {
+    typedef ScanNarrowCfg<In, Acc, Out> Cfg;
+    int a = cols, b = Cfg::VEC;
+    while (b) { const int r = a % b; a = b; b = r; }                  // a = gcd(cols, VEC)
+    const int q = cols / a;
+    const int active = kNarrowScanThreads / q * q;                    // active * VEC is a multiple of cols
+    const int64_t tile_elems = int64_t(active) * Cfg::VEC * Cfg::U;
+    const int64_t tiles = (n * cols + tile_elems - 1) / tile_elems;
+    static int occ = 0;                                               // per instantiation; benign race
+    if (!occ) {
+        int o = 0;
+        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, scan_narrow_kernel<In, Acc, Out, Op>, kNarrowScanThreads, 0);
+        occ = (e == cudaSuccess && o > 0) ? std::min(o, 8) : 4;
+    }
+    int64_t S = std::min<int64_t>(tiles, int64_t(sm_count) * occ);
+    const int64_t seg_tiles = (tiles + S - 1) / S;
+    S = (tiles + seg_tiles - 1) / seg_tiles;
+    Acc* tot = static_cast<Acc*>(ws);
+    if (S > 1) {
+        if (!ws || ws_bytes < size_t(S) * cols * sizeof(Acc))
+            return fail(B200_E_WORKSPACE, "scan_axis workspace %zu < %zu", ws_bytes, size_t(S) * cols * sizeof(Acc));
+        scan_narrow_totals_kernel<In, Acc, Out, Op><<<unsigned(S), kNarrowScanThreads, 0, s>>>(x, n, cols, active, seg_tiles, tot);
+    }
+    scan_narrow_kernel<In, Acc, Out, Op><<<unsigned(S), kNarrowScanThreads, 0, s>>>(x, y, n, cols, active, seg_tiles, tot);
+    B200_CUDA_TRY(cudaPeekAtLastError());
+    return 0;
+}
+
 // Strip width for the march: the widest of 512 / 256 / 128 bytes that still gives (nearly) one strip per SM; 0 when
 // even 128-byte strips leave more than half of the SMs idle (narrow matrices keep the split scheme).
 static int march_width(int64_t outer, int64_t inner_bytes, int sm_count) {
@@ -255,6 +303,8 @@ static int run_axis(const void* xv, void* yv, int64_t outer, int64_t n, int64_t 
             const unsigned grid = unsigned(std::min<int64_t>((outer + 7) / 8, int64_t(sm_count) * 8));
             scan_lines_kernel<In, Acc, Out, Op, 32, ITEMS><<<grid, 256, 0, s>>>(x, y, outer, n, in_vec, out_vec, nullptr, -1);
         }
+    } else if (narrow_scan_shape(outer, n, inner) && xa % 16 == 0 && ya % 16 == 0) {
+        return launch_narrow<In, Acc, Out, Op>(x, y, n, int(inner), ws, ws_bytes, sm_count, s);
     } else {
         constexpr int V = axis_vec<In, Out>();
         constexpr int in_al = int(sizeof(In)) * V >= 16 ? 16 : int(sizeof(In)) * V;
@@ -309,6 +359,7 @@ extern "C" __attribute__((visibility("default"))) int b200_scan_axis_workspace_b
     if (st) return st;
     const int64_t S = (outer == 0 || n == 0 || inner == 0) ? 1 : axis_split(outer, n, inner, di.sm_count);
     *bytes = S > 1 ? size_t(outer * S * inner) * 8 : 0;      // widest accumulator
+    if (outer > 0 && n > 0 && inner > 0 && narrow_scan_shape(outer, n, inner)) *bytes = std::max(*bytes, kNarrowScanWorkspace);
     return 0;
 }
 

@@ -1,4 +1,4 @@
-"""GPU tier: axis-0 reductions of tall, narrow matrices (rows of at most 128 elements: point clouds, feature
+"""GPU tier: axis-0 reductions of tall, narrow matrices (rows of at most 64 elements: point clouds, feature
 tables) -- the flat-stream kernel `reduce_narrow_body` (csrc/include/b200/reduce.cuh) -- against NumPy, over
 column counts that do and do not divide the vector width, ragged row counts, every prebuilt functor, planted
 ties and NaNs (first occurrence, NaN wins: tests/cupy_tests/sorting_tests/test_search.py:26-66)."""
@@ -96,3 +96,52 @@ def test_narrow_misaligned_base_and_views(cp):
     np.testing.assert_array_equal(d[1:].argmax(axis=0).get(), a[1:].argmax(axis=0))
     np.testing.assert_array_equal(d[4:].argmax(axis=0).get(), a[4:].argmax(axis=0))         # 48-byte offset: aligned again
     np.testing.assert_array_equal(d[:, :2].max(axis=0).get(), a[:, :2].max(axis=0))         # strided rows: generic route
+
+
+SCAN_SHAPES = [(100000, 3), (70001, 4), (50000, 7), (33333, 16), (20011, 33), (8193, 64), (300007, 2), (1 << 20, 5),
+               (65536, 1), (1100, 60), (2048, 32)]
+
+
+@pytest.mark.parametrize('dt', ['float32', 'float16', 'float64', 'int32', 'int64', 'int8', 'uint8', 'uint32', 'bool'])
+@pytest.mark.parametrize('shape', SCAN_SHAPES)
+def test_axis0_scans_of_narrow_matrices(cp, shape, dt):
+    """cumsum / cumprod along axis 0 of rows of at most 64 elements (scan_narrow.cuh): flat-stream tiles, one
+    segment per block, segment totals first.  Integers bit-exact; floats against a float64 scan."""
+    a = _data(shape, dt)
+    if np.dtype(dt).kind == 'f':
+        a = (a / 8).astype(dt)
+    d = cp.asarray(a)
+    want = np.cumsum(a, axis=0)
+    got = cp.cumsum(d, axis=0)
+    assert got.dtype == want.dtype and got.shape == want.shape
+    if np.dtype(dt).kind == 'f':
+        ref = np.cumsum(a.astype(np.float64), axis=0)
+        eps = {2: 1e-3, 4: 1.2e-7, 8: 2.3e-16}[np.dtype(dt).itemsize]
+        bound = eps * (np.abs(ref) + 1) + 4 * {2: 1.2e-7, 4: 1.2e-7, 8: 2.3e-16}[np.dtype(dt).itemsize] * np.cumsum(np.abs(a.astype('f8')), axis=0)
+        assert np.all(np.abs(got.get().astype('f8') - ref) <= bound)
+    else:
+        np.testing.assert_array_equal(got.get(), want)
+        # cumprod of {-1, 0, 1, 2}-ish values wraps in the result dtype exactly as NumPy's
+        b = (np.abs(a.astype(np.int64)) % 3 - 1 + (a.astype(np.int64) % 7 == 0)).astype(dt)
+        np.testing.assert_array_equal(cp.cumprod(cp.asarray(b), axis=0).get(), np.cumprod(b, axis=0))
+    # out= of another dtype, dtype=, in place, negative axis of the 2-d array
+    np.testing.assert_array_equal(cp.cumsum(d, axis=-2).get(), got.get())
+    if np.dtype(dt).kind in 'iu':
+        np.testing.assert_array_equal(cp.cumsum(d, axis=0, dtype=dt).get(), np.cumsum(a, axis=0, dtype=dt))
+    if dt in ('float32', 'int64'):
+        e = cp.asarray(a)
+        r = cp.cumsum(e, axis=0, out=e)
+        assert r is e
+        np.testing.assert_array_equal(e.get(), got.get())
+
+
+def test_narrow_scan_is_deterministic_and_matches_the_strip_route(cp, monkeypatch):
+    a = (RS.rand(1 << 19, 6) * 2 - 1).astype(np.float32)
+    d = cp.asarray(a)
+    first = cp.cumsum(d, axis=0).get()
+    for _ in range(3):
+        np.testing.assert_array_equal(cp.cumsum(d, axis=0).get(), first)         # bit-identical run to run
+    ref = np.cumsum(a.astype(np.float64), axis=0)
+    assert np.abs(first - ref).max() <= 1e-6 * np.abs(a).sum(axis=0).max()
+    # a row-offset view is not 16-byte aligned for every column count: the general route takes it
+    np.testing.assert_allclose(cp.cumsum(d[1:], axis=0).get(), np.cumsum(a[1:].astype('f8'), axis=0), rtol=1e-4, atol=1e-2)
