@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import ctypes
 
+import numpy
+
 from cupy_b200 import _lib
 from cupy_b200._core import _dryrun, _kernel, _scalar
 from cupy_b200._core._kernel import current_stream_ptr
@@ -31,6 +33,17 @@ def scan_axis(a, axis, op, dtype, out):
     if a.size == 0:
         return out if out is not None else ndarray(a.shape, dtype)
     src = a
+    if not _lib.lib.b200_scan_supported(op, in_id, out_id):
+        # no prebuilt (in, out) pair: scan in the widest accumulator of the result's kind (modular arithmetic
+        # commutes with the final truncation) and cast once at the end, as the flat route does
+        dt = numpy.dtype(dtype)
+        wide = numpy.dtype({'i': 'int64', 'b': 'int64', 'u': 'uint64'}.get(dt.kind, 'float64' if dt.itemsize == 8 else 'float32'))
+        if wide != dt and _lib.lib.b200_scan_supported(op, in_id, _scalar.dtype_id(wide)):
+            tmp = scan_axis(a, axis, op, wide, None)
+            if out is None:
+                out = ndarray(a.shape, dt)
+            _kernel.elementwise_copy(tmp, out)
+            return out
     if not _lib.lib.b200_scan_supported(op, in_id, out_id):
         # dtype pair without a prebuilt kernel: convert first (one extra pass), then scan in the out dtype
         src = ndarray(a.shape, dtype)

@@ -154,6 +154,27 @@ __device__ __forceinline__ void scan_narrow_body(const In* __restrict__ x, Out* 
         }
 
     const int64_t tile_first = int64_t(blockIdx.x) * seg_tiles;
+    // the loads of tile i + 1 are issued before tile i is scanned and wait in registers: a block alone keeps
+    // U vectors per thread in flight through all four phases (three or four blocks fit an SM, each of which would
+    // otherwise spend two thirds of its time with nothing outstanding)
+    Pack<In, VEC> pre[U];
+    auto fetch = [&](int64_t tl) {
+        const int64_t e0 = tl * tile_elems;
+        if (t < active && e0 < total) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t ge = e0 + u * chunk_elems + t * VEC;
+                if (ge + VEC <= total) {
+                    load_pack(pre[u], x + ge);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k)
+                        if (ge + k < total) pre[u][k] = x[ge + k];
+                }
+            }
+        }
+    };
+    fetch(tile_first);
     for (int64_t tl = tile_first; tl < tile_first + seg_tiles; ++tl) {
         const int64_t e0 = tl * tile_elems;
         if (e0 >= total) break;                          // block-uniform
@@ -165,18 +186,12 @@ __device__ __forceinline__ void scan_narrow_body(const In* __restrict__ x, Out* 
             for (int u = 0; u < U; ++u) {
                 const int f = u * chunk_elems + t * VEC;
                 const int64_t ge = e0 + f;
-                if (ge + VEC <= total) {
-                    Pack<In, VEC> v;
-                    load_pack(v, x + ge);
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) tile[narrow_pad(f + k)] = PipeCvt<In, Acc>::in(v[k]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k)
-                        tile[narrow_pad(f + k)] = ge + k < total ? PipeCvt<In, Acc>::in(x[ge + k]) : Op::template identity<Acc>();
-                }
+                for (int k = 0; k < VEC; ++k)
+                    tile[narrow_pad(f + k)] = ge + k < total ? PipeCvt<In, Acc>::in(pre[u][k]) : Op::template identity<Acc>();
             }
         }
+        if (tl + 1 < tile_first + seg_tiles) fetch(tl + 1);
         __syncthreads();
         // P2
         if (g < G) {

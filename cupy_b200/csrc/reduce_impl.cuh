@@ -291,9 +291,9 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
             const int active = narrow_active(cols, NV);
             const int64_t chunks = d->n_reduce / (int64_t(active) * NV / cols);
             // the last block folds grid * cols partials with 256 / cols threads per column: wider rows get fewer
-            // blocks (never under two per SM) so that this fold stays a few L2 round trips long
+            // blocks (never under four per SM) so that this fold stays a few L2 round trips long
             const int64_t resident = int64_t(di.sm_count) * narrow_blocks_per_sm<Op, NV, U>();
-            const int64_t fold_cap = std::max<int64_t>(2 * int64_t(di.sm_count), 16384 / cols);
+            const int64_t fold_cap = std::max<int64_t>(4 * int64_t(di.sm_count), 32768 / cols);
             const int grid = int(std::max<int64_t>(1, std::min<int64_t>((chunks + U - 1) / U, std::min(resident, fold_cap))));
             const size_t pbytes = size_t(grid) * cols * sizeof(acc_t);
             if (grid > 1 && ws_bytes < kTicketBytes + pbytes)

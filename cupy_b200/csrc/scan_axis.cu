@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kNarrowScanThreads) scan_narrow_totals_kernel(
     scan_narrow_totals_body<In, Acc, Out, Op>(x, n, cols, active, seg_tiles, tot);
 }
 template <class In, class Acc, class Out, class Op>
-__global__ void __launch_bounds__(kNarrowScanThreads) scan_narrow_kernel(const In* x, Out* y, int64_t n, int cols, int active,
+__global__ void __launch_bounds__(kNarrowScanThreads, 4) scan_narrow_kernel(const In* x, Out* y, int64_t n, int cols, int active,
                                                                          int64_t seg_tiles, const Acc* tot) {
     scan_narrow_body<In, Acc, Out, Op>(x, y, n, cols, active, seg_tiles, tot);
 }
