@@ -7,8 +7,8 @@
 // = chunk_rows whole rows, and a TILE is U chunks staged in shared memory as accumulators.  Inside a tile
 //   P1  coalesced vector loads -> shared memory (converted to the accumulator type),
 //   P2  thread (column c, group g) scans rows [g * L, (g + 1) * L) of column c in place (stride-cols walk),
-//   P3  one warp per column scans the G group totals, adds the running carry of the column, leaves each group's
-//       offset behind and advances the carry,
+//   P3  one warp per column (a thread per column when there are at most 8 groups) scans the G group totals, adds
+//       the running carry of the column, leaves each group's offset behind and advances the carry,
 //   P4  every thread re-reads ITS OWN flat elements, adds the offset of the group they fell in (indices that are
 //       the same for every tile: kept in registers) and stores 16..64-byte vectors, coalesced.
 // Across blocks it is reduce-then-scan, because that keeps floating-point results independent of timing: the
@@ -198,15 +198,31 @@ __device__ __forceinline__ void scan_narrow_body(const In* __restrict__ x, Out* 
             Acc a = Op::template identity<Acc>();
             const int r0 = g * L;
             const int r1 = r0 + L < rows_here ? r0 + L : rows_here;
-            for (int r = r0; r < r1; ++r) {
-                const int i = narrow_pad(r * cols + c);
-                a = Op::combine(a, tile[i]);
-                tile[i] = a;
+            for (int r = r0; r < r1; r += 8) {              // eight independent loads, then the dependent adds
+                Acc v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = r + j < r1 ? tile[narrow_pad((r + j) * cols + c)] : Op::template identity<Acc>();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    a = Op::combine(a, v[j]);
+                    if (r + j < r1) tile[narrow_pad((r + j) * cols + c)] = a;
+                }
             }
             groups[g * cols + c] = a;
         }
         __syncthreads();
         // P3
+        if (G <= 8) {                                    // few groups per column: a thread per column walks them
+            if (t < cols) {
+                Acc run = carry[t];
+                for (int gi = 0; gi < G; ++gi) {
+                    const Acc v = groups[gi * cols + t];
+                    groups[gi * cols + t] = run;
+                    run = Op::combine(run, v);
+                }
+                carry[t] = run;
+            }
+        } else
         for (int cc = warp; cc < cols; cc += T / 32) {
             Acc v[8];                                     // J <= 8: G <= 256
             Acc loc = Op::template identity<Acc>();
