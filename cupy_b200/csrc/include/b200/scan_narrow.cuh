@@ -198,15 +198,10 @@ __device__ __forceinline__ void scan_narrow_body(const In* __restrict__ x, Out* 
             Acc a = Op::template identity<Acc>();
             const int r0 = g * L;
             const int r1 = r0 + L < rows_here ? r0 + L : rows_here;
-            for (int r = r0; r < r1; r += 8) {              // eight independent loads, then the dependent adds
-                Acc v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = r + j < r1 ? tile[narrow_pad((r + j) * cols + c)] : Op::template identity<Acc>();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    a = Op::combine(a, v[j]);
-                    if (r + j < r1) tile[narrow_pad((r + j) * cols + c)] = a;
-                }
+            for (int r = r0; r < r1; ++r) {
+                const int i = narrow_pad(r * cols + c);
+                a = Op::combine(a, tile[i]);
+                tile[i] = a;
             }
             groups[g * cols + c] = a;
         }
