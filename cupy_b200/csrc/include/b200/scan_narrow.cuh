@@ -1,4 +1,4 @@
-// b200/scan_narrow.cuh -- cumsum / cumprod along axis 0 of a tall, narrow matrix x[n][cols] (cols <= 64: point
+// b200/scan_narrow.cuh -- cumsum / cumprod along axis 0 of a tall, narrow matrix x[n][cols] (cols <= 128: point
 // clouds, feature tables), where the strip kernels (scan_march.cuh, scan_cols_kernel) find no 128-byte strip to
 // give a warp and fall back to one element per thread: every 4-byte load drags a 32-byte sector, ~100 GB/s.
 //
@@ -7,7 +7,7 @@
 // = chunk_rows whole rows, and a TILE is U chunks staged in shared memory as accumulators.  Inside a tile
 //   P1  coalesced vector loads -> shared memory (converted to the accumulator type),
 //   P2  thread (column c, group g) scans rows [g * L, (g + 1) * L) of column c in place (stride-cols walk),
-//   P3  one warp per column (a thread per column when there are at most 8 groups) scans the G group totals, adds
+//   P3  one warp per column (a thread per column when there are at most 32 groups) scans the G group totals, adds
 //       the running carry of the column, leaves each group's offset behind and advances the carry,
 //   P4  every thread re-reads ITS OWN flat elements, adds the offset of the group they fell in (indices that are
 //       the same for every tile: kept in registers) and stores 16..64-byte vectors, coalesced.
@@ -22,7 +22,7 @@
 namespace b200 {
 
 constexpr int kNarrowScanThreads = 256;
-constexpr int kNarrowScanMaxCols = 64;
+constexpr int kNarrowScanMaxCols = 128;
 
 template <class In, class Acc, class Out>
 struct ScanNarrowCfg {
@@ -207,7 +207,7 @@ __device__ __forceinline__ void scan_narrow_body(const In* __restrict__ x, Out* 
         }
         __syncthreads();
         // P3
-        if (G <= 8) {                                    // few groups per column: a thread per column walks them
+        if (G <= 32) {                                   // few groups per column: a thread per column walks them
             if (t < cols) {
                 Acc run = carry[t];
                 for (int gi = 0; gi < G; ++gi) {

@@ -99,13 +99,13 @@ def test_narrow_misaligned_base_and_views(cp):
 
 
 SCAN_SHAPES = [(100000, 3), (70001, 4), (50000, 7), (33333, 16), (20011, 33), (8193, 64), (300007, 2), (1 << 20, 5),
-               (65536, 1), (1100, 60), (2048, 32)]
+               (65536, 1), (1100, 60), (2048, 32), (30011, 100), (9000, 128), (5000, 250), (4099, 256), (3000, 255)]
 
 
 @pytest.mark.parametrize('dt', ['float32', 'float16', 'float64', 'int32', 'int64', 'int8', 'uint8', 'uint32', 'bool'])
 @pytest.mark.parametrize('shape', SCAN_SHAPES)
 def test_axis0_scans_of_narrow_matrices(cp, shape, dt):
-    """cumsum / cumprod along axis 0 of rows of at most 64 elements (scan_narrow.cuh): flat-stream tiles, one
+    """cumsum / cumprod along axis 0 of rows of at most 128 elements (scan_narrow.cuh; wider ones take the strip routes): flat-stream tiles, one
     segment per block, segment totals first.  Integers bit-exact; floats against a float64 scan."""
     a = _data(shape, dt)
     if np.dtype(dt).kind == 'f':
