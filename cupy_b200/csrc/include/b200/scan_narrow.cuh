@@ -271,4 +271,83 @@ __device__ __forceinline__ void scan_narrow_body(const In* __restrict__ x, Out* 
     }
 }
 
+// ---- the same tiles for scans ALONG short rows (x[rows][len], len <= 64, scanning len) ------------------------------
+// A warp per row (scan_lines_kernel) leaves most lanes idle below 128 elements per row.  Here a tile is a whole number
+// of rows staged in shared memory with coalesced vector loads; a thread then walks whole rows (the padded layout keeps
+// the walks of a warp on different banks), and the tile goes back out coalesced.  Rows never cross a tile, so there
+// is no carry and no second pass: 8 bytes of traffic per 4-byte element, one launch.
+template <class In, class Acc, class Out, class Op>
+__device__ __forceinline__ void scan_short_rows_body(const In* __restrict__ x, Out* __restrict__ y, int64_t rows, int len,
+                                                     int active) {
+    typedef ScanNarrowCfg<In, Acc, Out> Cfg;
+    constexpr int T = Cfg::T, VEC = Cfg::VEC, U = Cfg::U, SLOTS = Cfg::SLOTS;
+    __shared__ __align__(16) Acc tile[SLOTS + SLOTS / 32 + 1];
+    const int t = threadIdx.x;
+    const int chunk_elems = active * VEC;
+    const int tile_elems = chunk_elems * U, tile_rows = tile_elems / len;
+    const int64_t total = rows * len;
+    const int64_t tiles = (total + tile_elems - 1) / tile_elems;
+    Pack<In, VEC> pre[U];
+    auto fetch = [&](int64_t tl) {
+        const int64_t e0 = tl * tile_elems;
+        if (t < active && tl < tiles) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t ge = e0 + u * chunk_elems + t * VEC;
+                if (ge + VEC <= total) {
+                    load_pack(pre[u], x + ge);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k)
+                        if (ge + k < total) pre[u][k] = x[ge + k];
+                }
+            }
+        }
+    };
+    fetch(blockIdx.x);
+    for (int64_t tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+        const int64_t e0 = tl * tile_elems;
+        if (t < active) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int f = u * chunk_elems + t * VEC;
+                const int64_t ge = e0 + f;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    tile[narrow_pad(f + k)] = ge + k < total ? PipeCvt<In, Acc>::in(pre[u][k]) : Op::template identity<Acc>();
+            }
+        }
+        fetch(tl + gridDim.x);
+        __syncthreads();
+        for (int r = t; r < tile_rows; r += T) {
+            Acc a = Op::template identity<Acc>();
+            const int base = r * len;
+            for (int j = 0; j < len; ++j) {
+                const int i = narrow_pad(base + j);
+                a = Op::combine(a, tile[i]);
+                tile[i] = a;
+            }
+        }
+        __syncthreads();
+        if (t < active) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int f = u * chunk_elems + t * VEC;
+                const int64_t ge = e0 + f;
+                Pack<Out, VEC> o;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) o[k] = static_cast<Out>(tile[narrow_pad(f + k)]);
+                if (ge + VEC <= total) {
+                    store_pack(y + ge, o);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k)
+                        if (ge + k < total) y[ge + k] = o[k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace b200

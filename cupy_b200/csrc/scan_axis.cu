@@ -211,6 +211,36 @@ __global__ void __launch_bounds__(kNarrowScanThreads, 4) scan_narrow_kernel(cons
     scan_narrow_body<In, Acc, Out, Op>(x, y, n, cols, active, seg_tiles, tot);
 }
 
+template <class In, class Acc, class Out, class Op>
+__global__ void __launch_bounds__(kNarrowScanThreads, 4) scan_short_rows_kernel(const In* x, Out* y, int64_t rows, int len, int active) {
+    scan_short_rows_body<In, Acc, Out, Op>(x, y, rows, len, active);
+}
+
+constexpr int kShortRowsMax = 64;
+static bool short_rows_shape(int64_t outer, int64_t n) {
+    static const bool off = getenv("B200_SCAN_NO_NARROW") != nullptr;          // A/B knob
+    return !off && n >= 2 && n <= kShortRowsMax && outer * n >= 65536;
+}
+
+static int narrow_scan_active(int cols, int vec) {
+    int a = cols, b = vec;
+    while (b) { const int r = a % b; a = b; b = r; }                  // a = gcd(cols, vec)
+    const int q = cols / a;
+    return kNarrowScanThreads / q * q;                                // active * vec is a multiple of cols
+}
+
+template <class In, class Acc, class Out, class Op>
+static int launch_short_rows(const In* x, Out* y, int64_t rows, int len, int sm_count, cudaStream_t s) {
+    typedef ScanNarrowCfg<In, Acc, Out> Cfg;
+    const int active = narrow_scan_active(len, Cfg::VEC);
+    const int64_t tile_elems = int64_t(active) * Cfg::VEC * Cfg::U;
+    const int64_t tiles = (rows * len + tile_elems - 1) / tile_elems;
+    const unsigned grid = unsigned(std::min<int64_t>(tiles, int64_t(sm_count) * 4));
+    scan_short_rows_kernel<In, Acc, Out, Op><<<grid, kNarrowScanThreads, 0, s>>>(x, y, rows, len, active);
+    B200_CUDA_TRY(cudaPeekAtLastError());
+    return 0;
+}
+
 static bool narrow_scan_shape(int64_t outer, int64_t n, int64_t inner) {
     static const bool off = getenv("B200_SCAN_NO_NARROW") != nullptr;          // A/B knob
     return !off && outer == 1 && inner >= 2 && inner <= kNarrowScanMaxCols && n * inner >= 65536;
@@ -220,10 +250,7 @@ constexpr size_t kNarrowScanWorkspace = size_t(296) * 8 * kNarrowScanMaxCols * 8
 template <class In, class Acc, class Out, class Op>
 static int launch_narrow(const In* x, Out* y, int64_t n, int cols, void* ws, size_t ws_bytes, int sm_count, cudaStream_t s) {
     typedef ScanNarrowCfg<In, Acc, Out> Cfg;
-    int a = cols, b = Cfg::VEC;
-    while (b) { const int r = a % b; a = b; b = r; }                  // a = gcd(cols, VEC)
-    const int q = cols / a;
-    const int active = kNarrowScanThreads / q * q;                    // active * VEC is a multiple of cols
+    const int active = narrow_scan_active(cols, Cfg::VEC);
     const int64_t tile_elems = int64_t(active) * Cfg::VEC * Cfg::U;
     const int64_t tiles = (n * cols + tile_elems - 1) / tile_elems;
     static int occ = 0;                                               // per instantiation; benign race
@@ -283,7 +310,9 @@ static int run_axis(const void* xv, void* yv, int64_t outer, int64_t n, int64_t 
     const In* x = static_cast<const In*>(xv);
     Out* y = static_cast<Out*>(yv);
     const uintptr_t xa = reinterpret_cast<uintptr_t>(xv), ya = reinterpret_cast<uintptr_t>(yv);
-    if (inner == 1) {
+    if (inner == 1 && short_rows_shape(outer, n) && xa % 16 == 0 && ya % 16 == 0) {
+        return launch_short_rows<In, Acc, Out, Op>(x, y, outer, int(n), sm_count, s);
+    } else if (inner == 1) {
         constexpr int ITEMS = (16 / int(sizeof(In))) < 4 ? 4 : (16 / int(sizeof(In)));
         constexpr int in_al = int(sizeof(In)) * ITEMS >= 16 ? 16 : int(sizeof(In)) * ITEMS;
         constexpr int out_al = int(sizeof(Out)) * ITEMS >= 16 ? 16 : int(sizeof(Out)) * ITEMS;

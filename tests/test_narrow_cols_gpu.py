@@ -145,3 +145,35 @@ def test_narrow_scan_is_deterministic_and_matches_the_strip_route(cp, monkeypatc
     assert np.abs(first - ref).max() <= 1e-6 * np.abs(a).sum(axis=0).max()
     # a row-offset view is not 16-byte aligned for every column count: the general route takes it
     np.testing.assert_allclose(cp.cumsum(d[1:], axis=0).get(), np.cumsum(a[1:].astype('f8'), axis=0), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize('dt', ['float32', 'float16', 'float64', 'int32', 'int64', 'int8', 'uint32', 'bool'])
+@pytest.mark.parametrize('shape', [(100000, 3), (70001, 4), (50000, 7), (33333, 16), (20011, 33), (8193, 64), (300007, 2),
+                                   (1 << 20, 5), (17, 4000, 6), (1100, 60)])
+def test_scans_along_short_rows(cp, shape, dt):
+    """cumsum / cumprod along the contiguous axis when rows have at most 64 elements (scan_short_rows_body: whole
+    rows staged in shared memory, a thread per row).  Rows are independent: every row is checked."""
+    a = _data(shape, dt)
+    if np.dtype(dt).kind == 'f':
+        a = (a / 2).astype(dt)
+    d = cp.asarray(a)
+    want = np.cumsum(a, axis=-1)
+    got = cp.cumsum(d, axis=-1)
+    assert got.dtype == want.dtype and got.shape == want.shape
+    if np.dtype(dt).kind == 'f':
+        ref = np.cumsum(a.astype(np.float64), axis=-1)
+        eps = {2: 1e-3, 4: 1.2e-7, 8: 2.3e-16}[np.dtype(dt).itemsize]
+        acc_eps = 1.2e-7 if np.dtype(dt).itemsize <= 4 else 2.3e-16
+        bound = eps * (np.abs(ref) + 1) + 2 * acc_eps * np.cumsum(np.abs(a.astype('f8')), axis=-1)
+        assert np.all(np.abs(got.get().astype('f8') - ref) <= bound)
+    else:
+        np.testing.assert_array_equal(got.get(), want)
+        b = (np.abs(a.astype(np.int64)) % 3 - 1 + (a.astype(np.int64) % 7 == 0)).astype(dt)
+        np.testing.assert_array_equal(cp.cumprod(cp.asarray(b), axis=-1).get(), np.cumprod(b, axis=-1))
+    if dt in ('float32', 'int64'):
+        e = cp.asarray(a)
+        assert cp.cumsum(e, axis=-1, out=e) is e
+        np.testing.assert_array_equal(e.get(), got.get())
+        o = cp.empty(shape, np.float64)
+        cp.cumsum(d, axis=-1, out=o)
+        np.testing.assert_allclose(o.get(), np.cumsum(a.astype('f8'), axis=-1), rtol=1e-5, atol=1e-4)
