@@ -608,6 +608,72 @@ __device__ __forceinline__ void reduce_narrow_body(
 }
 
 // ---------------------------------------------------------------------------
+// ROWS, short: x[rows][len] with len <= 64 (per-point norms, argmax over a few classes).  The group kernels above
+// give a row to 1 / 8 / 32 lanes and end up with one small load in flight per lane; here a tile of whole rows is
+// staged in shared memory with the flat stream's coalesced 16-byte loads (the next tile's loads already in flight),
+// and a thread then folds a whole row out of shared memory (the padded layout keeps the 32 walks of a warp on
+// different banks).  Results leave coalesced: consecutive threads own consecutive rows.
+// ---------------------------------------------------------------------------
+B200_DEVICE int short_pad(int i) { return i + (i >> 5); }
+
+template <class Op, int VEC, int U, int THREADS>
+__device__ __forceinline__ void reduce_short_rows_body(
+        const Op& op, const typename Op::in_t* __restrict__ x, typename Op::out_t* __restrict__ y,
+        int64_t rows, int len, int active) {
+    typedef typename Op::in_t in_t;
+    typedef typename Op::acc_t acc_t;
+    typedef typename Op::index_t index_t;
+    constexpr int SLOTS = THREADS * VEC * U;
+    __shared__ __align__(16) char tile_raw[(SLOTS + SLOTS / 32 + 1) * sizeof(in_t)];
+    in_t* tile = reinterpret_cast<in_t*>(tile_raw);
+    const int t = threadIdx.x;
+    const int chunk_elems = active * VEC;
+    const int tile_elems = chunk_elems * U, tile_rows = tile_elems / len;
+    const int64_t total = rows * len;
+    const int64_t tiles = (total + tile_elems - 1) / tile_elems;
+    Pack<in_t, VEC> pre[U];
+    auto fetch = [&](int64_t tl) {
+        if (t < active && tl < tiles) {
+            const int64_t e0 = tl * tile_elems;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t ge = e0 + u * chunk_elems + t * VEC;
+                if (ge + VEC <= total) {
+                    load_pack(pre[u], x + ge);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k)
+                        if (ge + k < total) pre[u][k] = x[ge + k];
+                }
+            }
+        }
+    };
+    fetch(blockIdx.x);
+    for (int64_t tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+        if (t < active) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int f = u * chunk_elems + t * VEC;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) tile[short_pad(f + k)] = pre[u][k];     // past the end: never read
+            }
+        }
+        fetch(tl + gridDim.x);
+        __syncthreads();
+        const int64_t row0 = tl * tile_rows;
+        const int64_t left = rows - row0;
+        const int here = left < tile_rows ? int(left) : tile_rows;
+        for (int r = t; r < here; r += THREADS) {
+            acc_t a = op.identity();
+            const int base = r * len;
+            for (int j = 0; j < len; ++j) op.accumulate(a, op.step(j + 1), tile[short_pad(base + j)], static_cast<index_t>(j));
+            y[row0 + r] = op.post(a, len);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // GENERIC: any strides, any number of (broadcast) inputs and outputs -- the
 // fallback for layouts that are none of FULL / ROWS / COLS and for user
 // ReductionKernels with several array operands (e.g. the reference's

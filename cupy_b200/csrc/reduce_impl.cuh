@@ -58,6 +58,12 @@ __global__ void __launch_bounds__(kRedThreads) reduce_narrow_kernel(
     reduce_narrow_body<Op, VEC, UNROLL, kRedThreads>(op, x, y, n, cols, active, partials, ticket);
 }
 
+template <class Op, int VEC, int U>
+__global__ void __launch_bounds__(kRedThreads) reduce_short_rows_kernel(
+        Op op, const typename Op::in_t* x, typename Op::out_t* y, int64_t rows, int len, int active) {
+    reduce_short_rows_body<Op, VEC, U, kRedThreads>(op, x, y, rows, len, active);
+}
+
 // ---- geometry ---------------------------------------------------------------
 struct Geometry {
     int vec;                 // chosen vector width
@@ -142,6 +148,13 @@ static void cols_geometry(int64_t batch, int64_t n, int64_t cols, int vec, int s
     g->gz = unsigned(batch);
     g->partial_count = nsplit > 1 ? size_t(batch) * nsplit * cols : 0;
     g->ticket_count = nsplit > 1 ? size_t(batch) * tiles : 0;
+}
+
+// short ROWS (reduce_short_rows_body): rows of 2..64 elements, enough of them to fill the device
+constexpr int kShortRowsMax = 64;
+static bool short_rows_shape(const b200_reduce_desc_t* d) {
+    static const bool off = getenv("B200_ROWS_NO_SHORT") != nullptr;           // A/B knob
+    return !off && d->n_reduce >= 2 && d->n_reduce <= kShortRowsMax && d->n_out * d->n_reduce >= 65536;
 }
 
 // narrow COLS (reduce_narrow_body): rows of at most 64 elements, one batch, enough rows to be worth a
@@ -253,6 +266,18 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
         return fail(B200_E_UNSUPPORTED, "reduced extent >= 2^31 is only prebuilt for the FULL layout");
     } else if (d->layout == B200_RED_ROWS) {
         if (query) { *need = 0; return 0; }
+        constexpr int SV = FULLVEC > 8 ? 8 : FULLVEC;                   // elements per load
+        constexpr int SU = (4096 / (kRedThreads * SV)) < 1 ? 1 : 4096 / (kRedThreads * SV);     // 4096 staged elements per tile
+        if (SV > 1 && short_rows_shape(d) && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+            const int len = int(d->n_reduce);
+            const int active = narrow_active(len, SV);
+            const int64_t tile_elems = int64_t(active) * SV * SU;
+            const int64_t tiles = (d->n_out * len + tile_elems - 1) / tile_elems;
+            const unsigned grid = unsigned(std::min<int64_t>(tiles, int64_t(di.sm_count) * 6));
+            reduce_short_rows_kernel<Op, SV, SU><<<grid, kRedThreads, 0, stream>>>(op, x, y, d->n_out, len, active);
+            B200_CUDA_TRY(cudaPeekAtLastError());
+            return 0;
+        }
         const int vec = pick_vec<FULLVEC>(x, d->n_reduce, sizeof(in_t));
         const int v = (vec == FULLVEC) ? FULLVEC : 1;
         // (measured at 32768^2: float16 argmax 84 -> 98 %, var 86 -> 96 % of peak with a warp per row; float32 loses 3-5 %)

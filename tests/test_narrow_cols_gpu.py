@@ -177,3 +177,45 @@ def test_scans_along_short_rows(cp, shape, dt):
         o = cp.empty(shape, np.float64)
         cp.cumsum(d, axis=-1, out=o)
         np.testing.assert_allclose(o.get(), np.cumsum(a.astype('f8'), axis=-1), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize('dt', ['float32', 'float16', 'float64', 'int32', 'int64', 'int8', 'uint8', 'bool'])
+@pytest.mark.parametrize('shape', [(100000, 3), (70001, 4), (50000, 7), (33333, 16), (20011, 33), (8193, 64), (300007, 2),
+                                   (1 << 20, 5), (17, 4000, 6), (1100, 60), (40000, 32)])
+def test_reductions_along_short_rows(cp, shape, dt):
+    """sum / max / argmax / mean / var ... along the contiguous axis when rows have at most 64 elements
+    (reduce_short_rows_body: whole rows staged in shared memory, a thread per row)."""
+    a = _data(shape, dt)
+    d = cp.asarray(a)
+    n = shape[-1]
+    kind = np.dtype(dt).kind
+    want = a.sum(axis=-1)
+    got = d.sum(axis=-1).get()
+    assert got.dtype == want.dtype and got.shape == want.shape
+    if kind == 'f':
+        tol = {2: 2e-3, 4: 1e-6, 8: 1e-14}[np.dtype(dt).itemsize]
+        ref = a.astype(np.float64).sum(axis=-1)
+        np.testing.assert_allclose(got.astype('f8'), ref, rtol=tol, atol=tol * n)
+        np.testing.assert_allclose(d.mean(axis=-1).get().astype('f8'), ref / n, rtol=tol, atol=tol)
+        np.testing.assert_allclose(d.var(axis=-1).get().astype('f8'), a.astype('f8').var(axis=-1), rtol=max(tol * 10, 1e-5), atol=tol)
+        np.testing.assert_allclose(d.var(axis=-1, ddof=1).get().astype('f8'), a.astype('f8').var(axis=-1, ddof=1),
+                                   rtol=max(tol * 10, 1e-5), atol=tol)
+    else:
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_allclose(d.mean(axis=-1).get(), a.mean(axis=-1), rtol=1e-12)
+        np.testing.assert_allclose(d.var(axis=-1).get(), a.var(axis=-1), rtol=1e-9, atol=1e-12)
+    for name in ('max', 'min', 'argmax', 'argmin', 'any', 'all'):
+        np.testing.assert_array_equal(getattr(d, name)(axis=-1).get(), getattr(a, name)(axis=-1), err_msg=name)
+    np.testing.assert_array_equal(d.prod(axis=-1).get() if kind != 'f' else 0, a.prod(axis=-1) if kind != 'f' else 0)
+    np.testing.assert_array_equal(d.max(axis=-1, keepdims=True).get(), a.max(axis=-1, keepdims=True))
+    if kind == 'f':
+        b = a.copy()
+        b[::7, n // 2] = np.nan
+        b[3::11, 0] = np.nan
+        b[5::13, n - 1] = np.nan
+        e = cp.asarray(b)
+        np.testing.assert_array_equal(e.argmax(axis=-1).get(), b.argmax(axis=-1))
+        np.testing.assert_array_equal(e.argmin(axis=-1).get(), b.argmin(axis=-1))
+        np.testing.assert_array_equal(e.max(axis=-1).get(), b.max(axis=-1))
+        c = np.round(a.astype('f8') * 2).astype(dt)            # few distinct values: ties, first occurrence wins
+        np.testing.assert_array_equal(cp.asarray(c).argmax(axis=-1).get(), c.argmax(axis=-1))
