@@ -109,9 +109,14 @@ static int full_blocks_per_sm() {
 
 // threads per row: the largest group whose unrolled tile (group * vec * unroll) still fits the row,
 // so that the row is read with full vector batches and not through the scalar tail loop
-static int rows_group(int64_t n, int vec, int unroll, bool heavy = false, int64_t rows = 0, int sm = 148) {
+static int rows_group(int64_t n, int vec, int unroll, bool heavy = false, int64_t rows = 0, int sm = 148,
+                      bool lane_state = false) {
     static const int forced = [] { const char* e = getenv("B200_ROWS_GROUP"); return e ? atoi(e) : 0; }();   // A/B knob
     if (forced == 256 || forced == 32 || forced == 8 || forced == 1) return forced;
+    // arg-reductions and moments on rows under 512 bytes: a thread per row.  Eight lanes per row leave each lane one
+    // or two vectors and then pay the lane merges (index / NaN bookkeeping, Chan) through shuffles for every row:
+    // rows of 32 float32 195 -> 65 us, of 64 110 -> 65 us, of 100 139 -> 88 us (profiles/r02_short_rows_probe.log)
+    if (lane_state && n < int64_t(32) * vec) return 1;
     // functors with a costly per-thread epilogue (arg-reductions: V lane merges with index and NaN handling;
     // moments: V Chan merges) amortise it over 8x more elements with a warp per row, when there are enough rows
     // to keep every warp of the device on its own row
@@ -150,11 +155,17 @@ static void cols_geometry(int64_t batch, int64_t n, int64_t cols, int vec, int s
     g->ticket_count = nsplit > 1 ? size_t(batch) * tiles : 0;
 }
 
-// short ROWS (reduce_short_rows_body): rows of 2..64 elements, enough of them to fill the device
+// short ROWS (reduce_short_rows_body): rows of 2..64 elements, enough of them to fill the device ...
 constexpr int kShortRowsMax = 64;
-static bool short_rows_shape(const b200_reduce_desc_t* d) {
+// ... and where the group kernels are at their worst (profiles/r02_short_rows_probe.log): rows of exactly one
+// 16-byte vector (one small load in flight per thread: 3.0 -> 3.8 TB/s, argmax 1.75 -> 3.4), and -- for functors
+// without lane state -- rows of 96..128 bytes, which fall between a thread per row and eight lanes per row
+static bool short_rows_shape(const b200_reduce_desc_t* d, int itemsize, bool lane_state) {
     static const bool off = getenv("B200_ROWS_NO_SHORT") != nullptr;           // A/B knob
-    return !off && d->n_reduce >= 2 && d->n_reduce <= kShortRowsMax && d->n_out * d->n_reduce >= 65536;
+    static const bool all = getenv("B200_ROWS_ALL_SHORT") != nullptr;          // A/B knob: every row length up to the cap
+    if (off || d->n_reduce < 2 || d->n_reduce > kShortRowsMax || d->n_out * d->n_reduce < 65536) return false;
+    const int64_t row_bytes = d->n_reduce * itemsize;
+    return all || row_bytes == 16 || (!lane_state && row_bytes >= 96 && row_bytes <= 128);
 }
 
 // narrow COLS (reduce_narrow_body): rows of at most 64 elements, one batch, enough rows to be worth a
@@ -268,7 +279,7 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
         if (query) { *need = 0; return 0; }
         constexpr int SV = FULLVEC > 8 ? 8 : FULLVEC;                   // elements per load
         constexpr int SU = (4096 / (kRedThreads * SV)) < 1 ? 1 : 4096 / (kRedThreads * SV);     // 4096 staged elements per tile
-        if (SV > 1 && short_rows_shape(d) && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+        if (SV > 1 && short_rows_shape(d, int(sizeof(in_t)), fast_lanes<Op>::value) && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
             const int len = int(d->n_reduce);
             const int active = narrow_active(len, SV);
             const int64_t tile_elems = int64_t(active) * SV * SU;
@@ -281,7 +292,8 @@ static int run_typed(const Op& op, const b200_reduce_desc_t* d, const void* xv, 
         const int vec = pick_vec<FULLVEC>(x, d->n_reduce, sizeof(in_t));
         const int v = (vec == FULLVEC) ? FULLVEC : 1;
         // (measured at 32768^2: float16 argmax 84 -> 98 %, var 86 -> 96 % of peak with a warp per row; float32 loses 3-5 %)
-        const int group = rows_group(d->n_reduce, v, U, fast_lanes<Op>::value && sizeof(in_t) <= 2, d->n_out, di.sm_count);
+        const int group = rows_group(d->n_reduce, v, U, fast_lanes<Op>::value && sizeof(in_t) <= 2, d->n_out, di.sm_count,
+                                     fast_lanes<Op>::value);
         const int64_t rows_per_block = kRedThreads / group;
         const int64_t blocks = (d->n_out + rows_per_block - 1) / rows_per_block;
         const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>(blocks, int64_t(di.sm_count) * 64)));
