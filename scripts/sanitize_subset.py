@@ -73,6 +73,32 @@ def main():
                                ((m2.astype(np.float64) - b.reshape(1024, 1024)) ** 2).sum(axis=1), rtol=1e-4)
     dot = cp.ReductionKernel('T p, T q', 'T r', 'p * q', 'a + b', 'r = a', '0', 'san_dot')
     np.testing.assert_allclose(dot(da, db).get(), (a.astype(np.float64) * b).sum(), rtol=1e-4)
+    # ---- narrow / short-row kernels (flat-stream tiles): reductions and scans along both axes, ufunc.at
+    for cols, dt in ((3, np.float32), (4, np.float32), (7, np.int32), (16, np.float16), (33, np.float64), (64, np.int8)):
+        rows = 70000 // cols * 3 + 5
+        p = (rs.rand(rows, cols) * 8 - 4).astype(dt)
+        dp = cp.asarray(p)
+        tol = 5e-2 if dt == np.float16 else 1e-4
+        np.testing.assert_allclose(dp.sum(axis=0).get().astype(np.float64), p.astype(np.float64).sum(axis=0), rtol=tol, atol=rows * tol)
+        np.testing.assert_array_equal(dp.argmax(axis=0).get(), p.argmax(axis=0))
+        np.testing.assert_array_equal(dp.argmax(axis=1).get(), p.argmax(axis=1))
+        np.testing.assert_array_equal(dp.max(axis=1).get(), p.max(axis=1))
+        np.testing.assert_allclose(dp.var(axis=0).get().astype(np.float64), p.astype(np.float64).var(axis=0), rtol=1e-2)
+        np.testing.assert_allclose(dp.var(axis=1).get().astype(np.float64), p.astype(np.float64).var(axis=1), rtol=1e-2, atol=1e-2)
+        if np.dtype(dt).kind == 'i':
+            np.testing.assert_array_equal(cp.cumsum(dp, axis=0).get(), np.cumsum(p, axis=0))
+            np.testing.assert_array_equal(cp.cumsum(dp, axis=1).get(), np.cumsum(p, axis=1))
+        else:
+            np.testing.assert_allclose(cp.cumsum(dp, axis=0).get().astype(np.float64), np.cumsum(p.astype(np.float64), axis=0),
+                                       rtol=tol, atol=rows * tol)
+            np.testing.assert_allclose(cp.cumsum(dp, axis=1).get().astype(np.float64), np.cumsum(p.astype(np.float64), axis=1),
+                                       rtol=tol, atol=cols * tol)
+    acc = np.zeros(1000, np.int64)
+    idx = rs.randint(0, 1000, 50000)
+    dacc = cp.asarray(acc)
+    cp.add.at(dacc, cp.asarray(idx), 1)
+    np.add.at(acc, idx, 1)
+    np.testing.assert_array_equal(dacc.get(), acc)
     torch.cuda.synchronize()
     print('sanitize subset ok')
 
