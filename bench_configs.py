@@ -468,6 +468,34 @@ def run_configs(peak, with_ref_gpu=True, quick=False):
         entries.append(_entry('sum axis=1 f32 rows of %d (%d rows)' % (cols, rows), 4 * rows * cols + 4 * rows, ms, peak,
                               ('ok' if err < 1e-3 else 'MISMATCH') + ' max_abs_err=%.1e' % err))
         del xr, tr
+    # tall narrow matrices (point clouds, feature tables, class scores): the flat-stream tile kernels
+    for rows, cols in ((1 << 26, 3), (1 << 23, 32)):
+        tn = torch.rand(rows, cols, device='cuda', generator=g) * 2 - 1
+        xn = cp.from_torch(tn)
+        nb = 4 * rows * cols
+        tag = 'f32 (%d, %d)' % (rows, cols)
+        ms, _ = _median_ms(lambda: xn.sum(axis=0), iters=it)
+        err = float((xn.sum(axis=0).to_torch().double() - tn.double().sum(0)).abs().max())
+        entries.append(_entry('sum axis=0 ' + tag, nb + 4 * cols, ms, peak,
+                              ('ok' if err < 1e-5 * rows else 'MISMATCH') + ' max_abs_err=%.1e' % err))
+        ms, _ = _median_ms(lambda: xn.var(axis=0), iters=it)
+        rel = float(((xn.var(axis=0).to_torch().double() - tn.double().var(0, unbiased=False)).abs() /
+                     tn.double().var(0, unbiased=False)).max())
+        entries.append(_entry('var axis=0 ' + tag, nb + 4 * cols, ms, peak, ('ok' if rel < 1e-5 else 'MISMATCH') + ' rel_err=%.1e' % rel))
+        ms, _ = _median_ms(lambda: xn.argmax(axis=1), iters=it)
+        same = bool(torch.equal(xn.argmax(axis=1).to_torch(), tn.argmax(1)))
+        entries.append(_entry('argmax axis=1 ' + tag, nb + 8 * rows, ms, peak, 'same indices' if same else 'MISMATCH'))
+        for ax in (0, 1):
+            ms, _ = _median_ms(lambda: cp.cumsum(xn, axis=ax), iters=it)
+            got = cp.cumsum(xn, axis=ax).to_torch()
+            ref = torch.cumsum(tn.double(), ax)
+            err = float((got.double() - ref).abs().max())
+            bound = 1e-6 * float(torch.cumsum(tn.double().abs(), ax).max())
+            entries.append(_entry('cumsum axis=%d %s' % (ax, tag), 2 * nb, ms, peak,
+                                  ('ok' if err <= bound else 'MISMATCH') + ' max_abs_err=%.1e (bound %.1e)' % (err, bound)))
+            del got, ref
+        del xn, tn
+        torch.cuda.empty_cache()
     src = cp.from_torch(t2)
     dst = cp.empty((16384, 32768), np.float32)
     dst_t = dst.to_torch()
