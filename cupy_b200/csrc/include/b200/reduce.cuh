@@ -374,7 +374,7 @@ __device__ __noinline__ void cols_fold_splits(const Op& op, const typename Op::a
     constexpr int kQuads = kBlockCols / VEC;              // WC * 32 packs across the tile
     constexpr int kLanes = kWarps * 32 / kQuads;          // == kWarpRows
     struct Q { acc_t v[VEC]; };
-    constexpr int kBatch = sizeof(Q) <= 16 ? 8 : (sizeof(Q) <= 32 ? 2 : 1);
+    constexpr int kBatch = sizeof(Q) <= 16 ? 8 : (sizeof(Q) <= 32 ? 2 : 1);  // more in flight costs the whole kernel registers
     const int q = threadIdx.x % kQuads, g = threadIdx.x / kQuads;
     const int64_t c = tile_c0 + int64_t(q) * VEC;
     const bool live = c < cols && g < nsplit;             // VEC > 1 => cols % VEC == 0 => whole pack in range
