@@ -516,11 +516,12 @@ __device__ __forceinline__ void reduce_cols_body(
 // ---------------------------------------------------------------------------
 template <class A> B200_DEVICE void shift_index(A&, long long) {}     // overloaded for (value, index) accumulators
 
-// column `c` of `count` row-major rows of accumulators starting at `rows`: the threads of a block are laid out
-// as (column, group); group gi folds rows gi, gi + G, ...; the groups' results then meet in `groups`
+// Column totals of `count` row-major rows of `cols` accumulators starting at `rows`: the threads of a block are laid
+// out as (column, group); group gi folds rows gi, gi + G, ...; the groups' results meet in `groups`.  The value
+// returned to thread t < cols is the total of column t (other threads get a don't-care).  Contains a barrier.
 template <class Op, int THREADS, bool FROM_GLOBAL>
 B200_DEVICE typename Op::acc_t fold_by_column(const Op& op, const typename Op::acc_t* rows, int count, int cols,
-                                              typename Op::acc_t* groups, bool* has_out) {
+                                              typename Op::acc_t* groups) {
     typedef typename Op::acc_t acc_t;
     const int t = threadIdx.x, G = THREADS / cols;
     const int c = t % cols, gi = t / cols;
@@ -543,7 +544,6 @@ B200_DEVICE typename Op::acc_t fold_by_column(const Op& op, const typename Op::a
         groups[gi * cols + c] = a;
     }
     __syncthreads();
-    *has_out = t < cols;
     acc_t r = groups[t < cols ? t : 0];
     if (t < cols) {
         const int used = count < G ? count : G;
@@ -602,8 +602,8 @@ __device__ __forceinline__ void reduce_narrow_body(
         }
     }
     __syncthreads();
-    bool mine;
-    acc_t r = fold_by_column<Op, THREADS, false>(op, lanes, chunk_rows, cols, groups, &mine);
+    const bool mine = t < cols;
+    acc_t r = fold_by_column<Op, THREADS, false>(op, lanes, chunk_rows, cols, groups);
     if (gridDim.x == 1) {
         if (mine) y[t] = op.post(r, n);
         return;
@@ -618,7 +618,7 @@ __device__ __forceinline__ void reduce_narrow_body(
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    r = fold_by_column<Op, THREADS, true>(op, partials, int(gridDim.x), cols, groups, &mine);
+    r = fold_by_column<Op, THREADS, true>(op, partials, int(gridDim.x), cols, groups);
     if (mine) y[t] = op.post(r, n);
 }
 
