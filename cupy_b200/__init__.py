@@ -24,7 +24,15 @@ from cupy_b200._core._routines_statistics import (  # noqa: F401
     amax, amin, argmax, argmin, mean, var, std)
 
 from cupy_b200._core._routines_more import (  # noqa: F401,E402
-    all, any, count_nonzero, nansum, nanprod, nanmin, nanmax, nanargmin, nanargmax, ptp)
+    all, any, count_nonzero, nansum, nanprod, nanmin, nanmax, nanargmin, nanargmax, ptp,
+    nanmean, nanvar, nanstd, nancumsum, nancumprod, average)
+from cupy_b200._core._routines_elementwise import (  # noqa: F401,E402
+    arcsin, arccos, arctan, arcsinh, arccosh, arctanh, deg2rad, rad2deg, radians, degrees,
+    logaddexp, logaddexp2, rint, floor, ceil, trunc, fix, around, round, round_,
+    reciprocal, positive, floor_divide, remainder, mod, divmod, fmod, modf, float_power,
+    signbit, copysign, nextafter, ldexp, frexp, cbrt, fabs, sign, heaviside, fmax, fmin,
+    clip, nan_to_num, gcd, lcm, logical_and, logical_or, logical_not, logical_xor,
+    isfinite, isinf, isnan, isneginf, isposinf, isclose, allclose, array_equal, where)
 from cupy_b200 import cuda  # noqa: F401,E402
 from cupy_b200._core.fusion import fuse  # noqa: F401,E402
 

@@ -630,8 +630,8 @@ class ndarray:
     def _binop(self, name, other, reflected=False):
         f = _UFUNCS.get(name)
         if f is None:
-            from cupy_b200._core import _routines_math as m, _routines_binary as b
-            f = _UFUNCS[name] = getattr(m, name, None) or getattr(b, name)
+            from cupy_b200._core import _routines_math as m, _routines_binary as b, _routines_elementwise as e
+            f = _UFUNCS[name] = getattr(m, name, None) or getattr(b, name, None) or getattr(e, name)
         to = type(other)
         if (to is ndarray or to is float or to is int or to is bool
                 or isinstance(other, (ndarray, int, float, bool, numpy.generic))
@@ -649,14 +649,22 @@ class ndarray:
     def __rtruediv__(self, o): return self._binop('true_divide', o, True)
 
     def _ibinop(self, name, other):
-        from cupy_b200._core import _routines_math as m, _routines_binary as b
-        (getattr(m, name, None) or getattr(b, name))(self, other, out=self)
+        from cupy_b200._core import _routines_math as m, _routines_binary as b, _routines_elementwise as e
+        (getattr(m, name, None) or getattr(b, name, None) or getattr(e, name))(self, other, out=self)
         return self
 
     def __iadd__(self, o): return self._ibinop('add', o)
     def __isub__(self, o): return self._ibinop('subtract', o)
     def __imul__(self, o): return self._ibinop('multiply', o)
     def __itruediv__(self, o): return self._ibinop('true_divide', o)
+    def __floordiv__(self, o): return self._binop('floor_divide', o)
+    def __rfloordiv__(self, o): return self._binop('floor_divide', o, True)
+    def __ifloordiv__(self, o): return self._ibinop('floor_divide', o)
+    def __mod__(self, o): return self._binop('remainder', o)
+    def __rmod__(self, o): return self._binop('remainder', o, True)
+    def __imod__(self, o): return self._ibinop('remainder', o)
+    def __divmod__(self, o): return self._binop('divmod', o)
+    def __rdivmod__(self, o): return self._binop('divmod', o, True)
 
     def __and__(self, o): return self._binop('bitwise_and', o)
     def __rand__(self, o): return self._binop('bitwise_and', o, True)
@@ -748,6 +756,14 @@ class ndarray:
     def any(self, axis=None, out=None, keepdims=False):
         from cupy_b200._core import _routines_more as r
         return r.any(self, axis, out, keepdims)
+
+    def clip(self, min=None, max=None, out=None):
+        from cupy_b200._core import _routines_elementwise as e
+        return e.clip(self, min, max, out=out)
+
+    def round(self, decimals=0, out=None):
+        from cupy_b200._core import _routines_elementwise as e
+        return e.around(self, decimals, out=out)
 
     def ptp(self, axis=None, out=None, keepdims=False):
         from cupy_b200._core import _routines_more as r

@@ -131,6 +131,34 @@ struct CSizeIndexer {
     __device__ ptrdiff_t size() const { return size_; }
 };
 
+// math.h constants user code strings spell (NVRTC has no host <cmath>; the reference gets them from
+// cupy/_core/include/cupy/math_constants.h through its own headers)
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+#ifndef M_E
+#define M_E 2.7182818284590452354
+#endif
+
+// `_floor_divide(x, y)`: the helper the reference's `floor_divide` / `remainder` / `divmod` routine strings
+// (and user kernels) call -- cupy/_core/include/cupy/carray.cuh:671-700.  Integers round toward minus
+// infinity and a zero divisor yields 0; floats are floor(x / y).
+template <class I>
+__device__ inline I _b200_floor_div_signed(I x, I y) {
+    if (y == 0) return 0;
+    const I q = x / y;
+    const I r = x - q * y;
+    return (r != 0 && ((r < 0) != (y < 0))) ? q - 1 : q;
+}
+__device__ inline int _floor_divide(int x, int y) { return _b200_floor_div_signed<int>(x, y); }
+__device__ inline long long _floor_divide(long long x, long long y) { return _b200_floor_div_signed<long long>(x, y); }
+__device__ inline unsigned _floor_divide(unsigned x, unsigned y) { return y == 0 ? 0u : x / y; }
+__device__ inline unsigned long long _floor_divide(unsigned long long x, unsigned long long y) {
+    return y == 0 ? 0ull : x / y;
+}
+__device__ inline float _floor_divide(float x, float y) { return floorf(x / y); }
+__device__ inline double _floor_divide(double x, double y) { return floor(x / y); }
+
 #ifndef CUPY_FOR
 #define CUPY_FOR(i, n)                                                        \
     for (ptrdiff_t i = static_cast<ptrdiff_t>(blockIdx.x) * blockDim.x + threadIdx.x; \
