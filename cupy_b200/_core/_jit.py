@@ -60,7 +60,10 @@ def _headers_digest():
 def compile_to_cubin(source, options=(), name='kernel.cu'):
     """source -> cubin bytes (no GPU needed: NVRTC cross-compiles for sm_100a)."""
     opts = tuple(default_options()) + tuple(options)
-    key = hashlib.sha1(('\0'.join(opts) + '\0' + _headers_digest() + '\0' + source).encode()).hexdigest()
+    # the checkout's own include directory is named by role, not by path (its CONTENT is in the header digest),
+    # so a cache survives moving or re-cloning the tree
+    key_opts = tuple('-I<b200/include>' if o == '-I' + _INCLUDE_DIR else o for o in opts)
+    key = hashlib.sha1(('\0'.join(key_opts) + '\0' + _headers_digest() + '\0' + source).encode()).hexdigest()
     use_disk = os.environ.get('CUPY_B200_CACHE_IN_MEMORY', '0') != '1'
     path = os.path.join(cache_dir(), key + '.cubin')
     if use_disk and os.path.exists(path):

@@ -348,12 +348,34 @@ _memo_epoch = 0
 tunables = _Tunables({
     'threads': 256,
     'flat_unroll': 4,
+    'flat_mixed_vec': 8,      # FLAT loops over operands of different item sizes: widest vector (elements) so the
+                              # narrow operand still moves >= 8 bytes per access; 0 = the planner's 16 / largest item
+                              # (B200 sweep profiles/r02_mixed_width_probe.log: where(mask, x, y) 73 -> 102 % of the
+                              # measured copy peak, isnan 89 -> 97 %; 16 is level with 8, 32 elements per thread lose)
+    'flat_mixed_items': 16,   # ... and elements per thread there (vector x unroll)
     'row_unroll': 2,
     'blocks_per_sm': 0,       # 0 = library default
     'tma_stages': 0,          # TILED_TMA ring depth, 0 = library default
     'reg_unroll': 0,          # TILED_REG blocks per thread, 0 = library default (8 vector loads in flight)
     'reg_min_blocks': 0,      # TILED_REG __launch_bounds__ min blocks/SM, 0 = from the register estimate
 })
+
+
+def _mixed_width_vector(args, ops, vec, unroll):
+    """FLAT loop over arrays of different item sizes (a comparison writing bool, `where` reading a mask, a cast):
+    the planner's vector is 16 bytes of the LARGEST item, which leaves the 1-byte operand with 4-byte accesses.
+    Widen the vector (wide operands then take several 16-byte accesses per step) while every operand keeps
+    the alignment its accesses need; the elements per thread stay what the tunables say."""
+    sizes = [args[k].dtype.itemsize for k, o in enumerate(ops) if o.kind == _lib.KIND_ARRAY]
+    if not sizes or min(sizes) == max(sizes):
+        return vec, unroll
+    want = min(tunables['flat_mixed_vec'], 16 // min(sizes))
+    while want > vec:
+        if all(args[k].ptr % min(16, want * args[k].dtype.itemsize) == 0
+               for k, o in enumerate(ops) if o.kind == _lib.KIND_ARRAY):
+            return want, max(1, tunables['flat_mixed_items'] // want)
+        want //= 2
+    return vec, unroll
 
 
 def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stream=None, ind_shape=None):
@@ -377,6 +399,9 @@ def _launch_jit(name, spec, args, params, n_in, ops, plan, block_size=None, stre
         unroll, vec = tunables['flat_unroll'], plan.vec
         if plan.staged_mask:          # periodic operands: the plan assumed 256-thread blocks
             threads = 256
+        elif tunables['flat_mixed_vec'] > vec > 1:
+            vec, unroll = _mixed_width_vector(args, ops, vec, unroll)
+            plan.vec = vec
     else:
         unroll, vec = tunables['row_unroll'], plan.vec
     arginfo = tuple(
