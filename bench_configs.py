@@ -512,6 +512,42 @@ def run_configs(peak, with_ref_gpu=True, quick=False):
                           'bit-exact' if ok else 'MISMATCH'))
     del t2, x2, src, dst, dst_t, wide, dense
     torch.cuda.empty_cache()
+
+    # ---------------- the widened elementwise family (cupy_b200/_core/_routines_elementwise.py) ----------------
+    # operands of different item sizes (bool masks) and the division / rounding / NaN-aware members, 2^28 float32
+    n = 1 << 28
+    tx = torch.rand(n, device='cuda', generator=g) * 8 - 4
+    ty = torch.rand(n, device='cuda', generator=g) * 3 + 1
+    tm = torch.rand(n, device='cuda', generator=g) > 0.5
+    tx[::97] = float('nan')
+    fx, fy, fm = cp.from_torch(tx), cp.from_torch(ty), cp.from_torch(tm)
+    fo = cp.empty((n,), np.float32)
+    fb = cp.empty((n,), np.bool_)
+
+    def same(got, want):
+        got = got.to_torch()
+        if got.dtype != want.dtype or got.shape != want.shape:
+            return 'MISMATCH (dtype / shape)'
+        if want.dtype == torch.float32:
+            ok = bool(((got == want) | (got.isnan() & want.isnan())).all())
+            return 'exact, NaNs in the same places' if ok else 'MISMATCH'
+        return 'bit-exact' if bool(torch.equal(got, want)) else 'MISMATCH'
+    for name, f, want, nbytes in (
+            ('where(mask, x, y) f32 2^28 (bool mask + two operands)', lambda: cp.where(fm, fx, fy), lambda: torch.where(tm, tx, ty), 13 * n),
+            ('greater(x, y) -> bool f32 2^28', lambda: cp.greater(fx, fy, out=fb), lambda: tx > ty, 9 * n),
+            ('isnan(x) -> bool f32 2^28', lambda: cp.isnan(fx, out=fb), lambda: torch.isnan(tx), 5 * n),
+            ('floor_divide(x, y) f32 2^28', lambda: cp.floor_divide(fx, fy, out=fo), lambda: torch.floor(tx / ty), 12 * n),
+            ('clip(x, -1, 1) f32 2^28', lambda: cp.clip(fx, -1, 1, out=fo), lambda: torch.clamp(tx, -1, 1), 8 * n),
+            ('floor(x) f32 2^28', lambda: cp.floor(fx, out=fo), lambda: torch.floor(tx), 8 * n)):
+        ms, _ = _median_ms(f, iters=it)
+        entries.append(_entry(name, nbytes, ms, peak, same(f(), want())))
+    ms, _ = _median_ms(lambda: cp.nanmean(fx), iters=it)
+    ref = float(torch.nanmean(tx.double()))
+    err = abs(float(cp.nanmean(fx).get()) - ref)
+    entries.append(_entry('nanmean(x) f32 2^28 (full; sum and count of the non-NaN elements in one pass)', 4 * n, ms, peak,
+                          ('ok' if err < 1e-5 else 'MISMATCH') + ' abs_err=%.1e' % err))
+    del tx, ty, tm, fx, fy, fm, fo, fb
+    torch.cuda.empty_cache()
     return entries, ref_note
 
 
