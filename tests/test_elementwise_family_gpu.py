@@ -312,6 +312,29 @@ def test_where(cp, dt):
         cp.where(cp.asarray(m), cp.asarray(x))
 
 
+@pytest.mark.parametrize('n', [1, 7, 8, 9, 4095, 100003, (1 << 20) + 5])
+def test_mixed_item_sizes_any_alignment(cp, n):
+    """Loops over operands of different item sizes widen their vector (tunables['flat_mixed_vec']) only while
+    every operand keeps the alignment its accesses need: views starting at odd offsets, ragged tails."""
+    x = uniform(-4, 4, 'float32', (n + 16,))
+    y = uniform(-4, 4, 'float32', (n + 16,))
+    m = RS.rand(n + 16) > 0.5
+    h = uniform(-4, 4, 'float16', (n + 16,))
+    x[::5] = np.nan
+    dx, dy, dm, dh = cp.asarray(x), cp.asarray(y), cp.asarray(m), cp.asarray(h)
+    for ox, om in ((0, 0), (1, 0), (0, 1), (4, 4), (0, 8), (3, 5), (8, 16), (2, 2)):
+        sx, sy, sm, sh = slice(ox, ox + n), slice(ox, ox + n), slice(om, om + n), slice(om, om + n)
+        np.testing.assert_array_equal(cp.where(dm[sm], dx[sx], dy[sy]).get(), np.where(m[sm], x[sx], y[sy]))
+        np.testing.assert_array_equal(cp.isnan(dx[sx]).get(), np.isnan(x[sx]))
+        np.testing.assert_array_equal(cp.greater(dx[sx], dy[sy]).get(), x[sx] > y[sy])
+        np.testing.assert_array_equal(cp.add(dx[sx], dh[sh]).get(), x[sx] + h[sh])            # float32 + float16
+        out = cp.asarray(np.zeros(n + 16, dtype=bool))
+        cp.less(dx[sx], 0, out=out[sm])
+        want = np.zeros(n + 16, dtype=bool)
+        want[sm] = x[sx] < 0
+        np.testing.assert_array_equal(out.get(), want)                                        # nothing outside the view
+
+
 # ---------------------------------------------------------------------------------------------
 # logic
 # ---------------------------------------------------------------------------------------------
