@@ -33,6 +33,8 @@ from cupy_b200._core._routines_elementwise import (  # noqa: F401,E402
     signbit, copysign, nextafter, ldexp, frexp, cbrt, fabs, sign, heaviside, fmax, fmin,
     clip, nan_to_num, gcd, lcm, logical_and, logical_or, logical_not, logical_xor,
     isfinite, isinf, isnan, isneginf, isposinf, isclose, allclose, array_equal, where)
+from cupy_b200._core._compaction import (  # noqa: F401,E402
+    nonzero, argwhere, flatnonzero, compress, extract, take)
 from cupy_b200 import cuda  # noqa: F401,E402
 from cupy_b200._core.fusion import fuse  # noqa: F401,E402
 

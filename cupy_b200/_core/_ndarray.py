@@ -407,11 +407,13 @@ class ndarray:
         return self._view(shape, tuple(strides))
 
     def __getitem__(self, key):
-        """Basic indexing only (ints, slices, None, Ellipsis): views, never copies."""
+        """Basic indexing (ints, slices, None, Ellipsis) gives views.  Index ARRAYS -- one boolean mask, or integer
+        arrays for the leading axes -- copy through the compaction / gather kernels (_core/_compaction.py)."""
         if not isinstance(key, tuple):
             key = (key,)
         if any(isinstance(k, (list, numpy.ndarray, ndarray)) for k in key):
-            raise NotImplementedError('advanced indexing is outside the elementwise/reduction hot path')
+            from cupy_b200._core import _compaction
+            return _compaction.getitem_advanced(self, key)
         n_real = sum(1 for k in key if k is not None and k is not Ellipsis)
         if n_real > self.ndim:
             raise IndexError('too many indices for array')
@@ -445,6 +447,9 @@ class ndarray:
 
     def __setitem__(self, key, value):
         from cupy_b200._core import _kernel
+        if any(isinstance(k, (list, numpy.ndarray, ndarray)) for k in (key if isinstance(key, tuple) else (key,))):
+            from cupy_b200._core import _compaction
+            return _compaction.setitem_advanced(self, key, value)
         dst = self[key]
         _kernel.elementwise_copy(value, dst)
 
@@ -756,6 +761,18 @@ class ndarray:
     def any(self, axis=None, out=None, keepdims=False):
         from cupy_b200._core import _routines_more as r
         return r.any(self, axis, out, keepdims)
+
+    def nonzero(self):
+        from cupy_b200._core import _compaction
+        return _compaction.nonzero(self)
+
+    def take(self, indices, axis=None, out=None):
+        from cupy_b200._core import _compaction
+        return _compaction.take(self, indices, axis=axis, out=out)
+
+    def compress(self, condition, axis=None, out=None):
+        from cupy_b200._core import _compaction
+        return _compaction.compress(condition, self, axis=axis, out=out)
 
     def clip(self, min=None, max=None, out=None):
         from cupy_b200._core import _routines_elementwise as e

@@ -16,7 +16,7 @@ which dtype comes out, what happens on zero divisors, NaNs, signed zeros):
   logical_and/or/not/xor       cupy/_logic/ops.py:6-46, cupy/_core/_routines_logic.pyx:101-118
   isfinite isinf isnan isneginf isposinf   cupy/_logic/content.py:9-135
   isclose allclose array_equal   cupy/_logic/comparison.py:10-132
-  where (three-argument form)  cupy/_sorting/search.py:167-210
+  where                        cupy/_sorting/search.py:167-210 (one-argument form: _core/_compaction.py)
 """
 from __future__ import annotations
 
@@ -329,11 +329,12 @@ _where_ufunc = create_ufunc('cupy_where', tuple('?%s%s->%s' % (c, c, c) for c in
 
 
 def where(condition, x=None, y=None):
-    """Elements of x where `condition` holds, of y elsewhere.  The one-argument form (`nonzero`) is
-    index generation, outside this package's path."""
+    """Elements of x where `condition` holds, of y elsewhere; `where(condition)` alone is `nonzero(condition)`
+    (the scan-based compaction of _core/_compaction.py)."""
     missing = (x is None, y is None)
     if missing == (True, True):
-        raise NotImplementedError('where(condition) alone is nonzero(): not part of the elementwise path')
+        from cupy_b200._core import _compaction
+        return _compaction.nonzero(condition)
     if missing != (False, False):
         raise ValueError('Must provide both \'x\' and \'y\' or neither.')
     condition = _math._as_array(condition)

@@ -10,6 +10,7 @@
     X(B200_TYPE_INT8, B200_TYPE_INT64, int8_t, long long, long long)     \
     X(B200_TYPE_INT8, B200_TYPE_INT8, int8_t, int32_t, int8_t)            \
     X(B200_TYPE_BOOL, B200_TYPE_INT64, bool, long long, long long)       \
+    X(B200_TYPE_BOOL, B200_TYPE_INT32, bool, int32_t, int32_t)           \
     X(B200_TYPE_UINT8, B200_TYPE_UINT64, uint8_t, unsigned long long, unsigned long long)   \
     X(B200_TYPE_UINT16, B200_TYPE_UINT64, uint16_t, unsigned long long, unsigned long long) \
     X(B200_TYPE_UINT32, B200_TYPE_UINT64, uint32_t, unsigned long long, unsigned long long) \
