@@ -107,8 +107,6 @@ def test_wrappers_route_like_the_reference(dry):
     assert names(dry) == ['cupy_where', 'cupy_not_equal', 'cupy_where']
     with pytest.raises(ValueError):
         cp.where(b, f)
-    with pytest.raises(NotImplementedError):
-        cp.where(b)
     # isclose on integers compares in float64
     del dry[:]
     assert cp.isclose(i, i).dtype == np.bool_
