@@ -546,9 +546,29 @@ def run_configs(peak, with_ref_gpu=True, quick=False):
     err = abs(float(cp.nanmean(fx).get()) - ref)
     entries.append(_entry('nanmean(x) f32 2^28 (full; sum and count of the non-NaN elements in one pass)', 4 * n, ms, peak,
                           ('ok' if err < 1e-5 else 'MISMATCH') + ' abs_err=%.1e' % err))
-    del tx, ty, tm, fx, fy, fm, fo, fb
+    del ty, tm, fy, fm, fo, fb
+    entries.extend(compaction_rows(cp, torch, fx, tx, peak, it))
+    del tx, fx
     torch.cuda.empty_cache()
     return entries, ref_note
+
+
+def compaction_rows(cp, torch, fx, tx, peak, it):
+    """The scan's callers (cupy_b200/_core/_compaction.py) on 2^28 float32: flags -> int32 ranks (prebuilt
+    bool -> int32 scan) -> one scatter; each call reads the hit count back once, as the reference does
+    (cupy/_core/_routines_indexing.pyx:123).  Bytes = the input read once + the compacted output written once."""
+    n = fx.size
+    rows = []
+    hits = int((tx > 0.75).sum())
+    ms, _ = _median_ms(lambda: cp.flatnonzero(fx > 0.75), iters=it)
+    ok = bool(torch.equal(cp.flatnonzero(fx > 0.75).to_torch(), torch.nonzero(tx > 0.75).flatten()))
+    rows.append(_entry('flatnonzero(x > 0.75) f32 2^28 (compare + rank scan + scatter, one count read-back; %d hits)' % hits,
+                       4 * n + 8 * hits, ms, peak, 'bit-exact' if ok else 'MISMATCH', launches=3))
+    ms, _ = _median_ms(lambda: fx[fx > 0.75], iters=it)
+    ok = bool(torch.equal(fx[fx > 0.75].to_torch(), tx[tx > 0.75]))
+    rows.append(_entry('x[x > 0.75] f32 2^28 (boolean-mask select: compare + rank scan + gather)', 4 * n + 4 * hits, ms, peak,
+                       'bit-exact' if ok else 'MISMATCH', launches=3))
+    return rows
 
 
 def oracle_cindexer(shape):

@@ -53,3 +53,10 @@ for name, f, nbytes in cases:
     ms = timed(f)
     gbs = nbytes / ms / 1e6
     print(json.dumps({'case': name + ' f32 2^28', 'ms': round(ms, 4), 'GBps': round(gbs, 1), 'pct_of_measured_peak': round(100 * gbs / PEAK, 1)}))
+
+# the compaction rows of the bench `configs` table, through the very function bench.py calls
+import bench_configs  # noqa: E402
+tx = torch.rand(n, device='cuda') * 8 - 4
+tx[::97] = float('nan')
+for e in bench_configs.compaction_rows(cp, torch, cp.from_torch(tx), tx, PEAK, 10):
+    print(json.dumps(e))
