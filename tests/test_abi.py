@@ -193,6 +193,8 @@ def test_scan_support_and_workspace():
     assert _lib.lib.b200_scan_supported(_lib.OP_CUMSUM, _lib.TYPE_INT64, _lib.TYPE_INT64) == 1
     assert _lib.lib.b200_scan_supported(_lib.OP_CUMSUM, _lib.TYPE_INT32, _lib.TYPE_INT64) == 1
     assert _lib.lib.b200_scan_supported(_lib.OP_CUMPROD, F32, F32) == 1
+    # the pair a compaction ranks its flags with (cupy_b200/_core/_compaction.py)
+    assert _lib.lib.b200_scan_supported(_lib.OP_CUMSUM, _lib.TYPE_BOOL, _lib.TYPE_INT32) == 1
     assert _lib.lib.b200_scan_supported(_lib.OP_SUM, F32, F32) == 0
     need = ctypes.c_size_t()
     assert _lib.lib.b200_scan_workspace_bytes(1 << 28, _lib.TYPE_INT64, ctypes.byref(need)) == 0
