@@ -180,9 +180,7 @@ def extract(condition, a):
 def take(a, indices, axis=None, out=None):
     """a[..., indices, ...] along `axis` (the flattened array when None); negative indices wrap once, out-of-range
     ones wrap around like the reference's (`mode='wrap'`-like, no bounds check on the device)."""
-    from cupy_b200._core import _kernel
-    from cupy_b200._core._ndarray import ndarray, asarray, empty
-    from cupy_b200._core._ndarray import normalize_axis_index
+    from cupy_b200._core._ndarray import ndarray, asarray, empty, normalize_axis_index
     a = _math._as_array(a)
     if not isinstance(indices, ndarray):
         indices = asarray(numpy.asarray(indices))

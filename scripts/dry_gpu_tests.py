@@ -8,7 +8,6 @@ What it proves: the calls the GPU tier will make are accepted by the host path a
 compiles.  With CUPY_B200_CACHE_DIR pointing into the tree it also leaves the cubins behind, so a later run of
 the same file on the GPU box (from the same path) starts warm.  TEST INFRASTRUCTURE, never a product path."""
 import ast
-import importlib.util
 import inspect
 import itertools
 import os
