@@ -115,6 +115,72 @@ def ulp_diff(got, want):
 
 
 # ---------------------------------------------------------------------------
+# the division / rounding members of the elementwise family: the places where the reference's
+# routine text is NOT NumPy's algorithm (cupy_b200/_core/_routines_elementwise.py follows the reference)
+# ---------------------------------------------------------------------------
+def floor_divide(x, y):
+    """cupy/_core/include/cupy/carray.cuh:671-700 `_floor_divide`: integers round toward minus infinity and a zero
+    divisor yields 0; floats are floor(x / y) in the operand precision (NumPy derives the float quotient from
+    fmod, which differs when x / y rounds up to an integer)."""
+    x, y = np.asarray(x), np.asarray(y)
+    dt = np.result_type(x, y)
+    x, y = x.astype(dt), y.astype(dt)
+    with np.errstate(all='ignore'):
+        if dt.kind == 'f':
+            ct = np.float32 if dt == np.float16 else dt        # float16 operands compute in float
+            return np.floor(x.astype(ct) / y.astype(ct)).astype(dt)
+        safe = np.where(y == 0, 1, y)
+        q = np.floor_divide(x, safe)
+        return np.where(y == 0, 0, q).astype(dt)
+
+
+def remainder(x, y):
+    """cupy/_core/_routines_math.pyx:1099-1110: `in0 - _floor_divide(in0, in1) * in1`, times `(in1 != 0)` for
+    integers.  (The device compiler may contract the float form into one FMA -- a single rounding -- so bit equality
+    with this two-rounding restatement holds where q * y is exact, which is the domain the parity tests use.)"""
+    x, y = np.asarray(x), np.asarray(y)
+    dt = np.result_type(x, y)
+    x, y = x.astype(dt), y.astype(dt)
+    with np.errstate(all='ignore'):
+        if dt.kind == 'f':
+            ct = np.float32 if dt == np.float16 else dt
+            q = np.floor(x.astype(ct) / y.astype(ct))
+            return (x.astype(ct) - q * y.astype(ct)).astype(dt)
+        return (x - floor_divide(x, y) * y) * (y != 0)
+
+
+def around_int(x, decimals):
+    """Integers rounded to a negative number of decimals: cupy/_core/core.pyx:2796-2814 `_round_ufunc_neg_uint`
+    (split at the last two digits of the scaled value, round those half to even in float, unscale)."""
+    x = np.asarray(x)
+    assert x.dtype.kind in 'iu' and decimals < 0
+    d = -decimals
+    scale = np.int64(10) ** (d - 1)
+    xi = x.astype(np.int64)
+    q = (np.abs(xi) // scale // 100) * np.sign(xi)             # C division truncates toward zero
+    r = (xi - q * scale * 100).astype(np.int32)
+    t = np.rint(r.astype(np.float32) / np.float32(scale * 10.0)).astype(np.int64)
+    return ((q * 100 + t * 10) * scale).astype(x.dtype)
+
+
+def sign(x):
+    """cupy/_math/misc.py:224-262: integers (x > 0) - (x < 0); floats copysign(1, x) off zero, x - x at zero and NaN
+    (so sign(-0.) is +0., NaN stays NaN)."""
+    x = np.asarray(x)
+    if x.dtype.kind == 'f':
+        with np.errstate(invalid='ignore'):
+            return np.where((x < 0) | (x > 0), np.copysign(x.dtype.type(1), x), x - x).astype(x.dtype)
+    return ((x > 0).astype(np.int64) - (x < 0).astype(np.int64)).astype(x.dtype)
+
+
+def clip(x, lo, hi):
+    """cupy/_core/_routines_math.pyx:1146-1151: `lo > hi ? hi : (x < lo ? lo : (x > hi ? hi : x))`."""
+    x = np.asarray(x)
+    lo, hi = np.asarray(lo, x.dtype), np.asarray(hi, x.dtype)
+    return np.where(lo > hi, hi, np.where(x < lo, lo, np.where(x > hi, hi, x))).astype(x.dtype)
+
+
+# ---------------------------------------------------------------------------
 # reductions
 # ---------------------------------------------------------------------------
 def sum_dtype(dtype):

@@ -137,3 +137,54 @@ def test_cumsum_int_is_exact_and_wraps():
     oracle.clib().oracle_cumsum_i64(a.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
                                     out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 3)
     np.testing.assert_array_equal(out, got)
+
+
+# ---------------------------------------------------------------------------------------------
+# division / rounding members of the elementwise family: the oracle restates the REFERENCE's routine text
+# (which is not always NumPy's algorithm); pinned on the reference's own border cases and on NumPy wherever the
+# two definitions must agree -- the domain the GPU tier (tests/test_elementwise_family_gpu.py) draws from
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('value,decimals', [(14, -1), (15, -1), (16, -1), (-14, -1), (-15, -1), (-16, -1),
+                                            (25, -1), (35, -1), (149, -2), (150, -2), (250, -2), (99999, -2), (7, -3)])
+def test_oracle_around_int_border_cases(value, decimals):
+    """tests/cupy_tests/math_tests/test_rounding.py:131-166 `TestRoundBorder` (14 / 15 / 16 at -1, both signs):
+    the digit-splitting routine agrees with NumPy's half-to-even."""
+    for dt in ('int32', 'int64'):
+        a = np.array([value], dt)
+        np.testing.assert_array_equal(oracle.around_int(a, decimals), np.around(a, decimals))
+
+
+def test_oracle_division_family_agrees_with_numpy_on_the_test_domain():
+    rs = np.random.RandomState(3)
+    for dt in ('int8', 'uint8', 'int16', 'int32', 'uint32', 'int64', 'uint64'):
+        lo = 0 if np.dtype(dt).kind == 'u' else -60
+        x = rs.randint(lo, 60, size=5000).astype(dt)
+        y = rs.randint(lo, 60, size=5000).astype(dt)              # zeros included: both give 0
+        with np.errstate(divide='ignore'):
+            np.testing.assert_array_equal(oracle.floor_divide(x, y), np.floor_divide(x, y))
+            np.testing.assert_array_equal(oracle.remainder(x, y), np.remainder(x, y))
+    for dt in ('float16', 'float32', 'float64'):
+        x = (rs.randint(-50, 50, size=5000) / 4).astype(dt)       # quarter-valued: quotients exact or far from an integer
+        y = rs.randint(1, 9, size=5000).astype(dt) * rs.choice([-1, 1], size=5000).astype(dt)
+        np.testing.assert_array_equal(oracle.floor_divide(x, y), np.floor_divide(x, y))
+        np.testing.assert_array_equal(oracle.remainder(x, y), np.remainder(x, y))
+
+
+def test_oracle_records_where_the_reference_leaves_numpy():
+    """floor(x / y) against NumPy's fmod-based quotient: when x / y rounds UP to an integer the reference's answer
+    is one larger (and its remainder is then about zero instead of about y).  The GPU tier stays off
+    this set; the oracle states which side the engine is on."""
+    x, y = np.float32(0.7), np.float32(0.1)                      # 0.7f / 0.1f rounds to 7.0f; exactly it is 6.9999998
+    assert fractions.Fraction(float(x)) / fractions.Fraction(float(y)) < 7
+    assert np.floor_divide(x, y) == 6.0
+    assert oracle.floor_divide(x, y) == 7.0
+    assert abs(oracle.remainder(x, y)) < 1e-6 and np.remainder(x, y) > 0.09      # 0.7 - 7 * 0.1 against 0.7 - 6 * 0.1
+    # sign(-0.) is +0. (x - x), NaN stays NaN; clip with lo > hi is hi everywhere -- both as NumPy
+    s = np.array([0.0, -0.0, np.nan, -2.5, 3.0], 'float32')
+    np.testing.assert_array_equal(oracle.sign(s), np.sign(s))
+    assert not np.signbit(oracle.sign(s)[1])
+    for dt in ('int8', 'uint16', 'int64'):
+        a = np.arange(0, 100, 7).astype(dt)
+        np.testing.assert_array_equal(oracle.sign(a), np.sign(a))
+        np.testing.assert_array_equal(oracle.clip(a, 20, 60), np.clip(a, 20, 60))
+        np.testing.assert_array_equal(oracle.clip(a, 60, 20), np.clip(a, 60, 20))
